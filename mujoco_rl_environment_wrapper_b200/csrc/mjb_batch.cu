@@ -1,0 +1,294 @@
+// mjb_batch.cu — CUDA half of the C-ABI (include/mjb.h): the persistent warp-per-env kernel and the
+// batch handle.  sm_100a only; there is no CPU fallback (creation fails without a device).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mjb.h"
+#include "dev_model_build.h"
+#include "env_kernel.cuh"
+#include "mjb_internal.h"
+
+namespace mjb {
+
+// ---- TMA bulk copy of the constant image into shared memory (SASS: UBLKCP + SYNCS) ---------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// One CTA per SM slot, `warps` environments in flight per CTA; each warp walks the env index space
+// with a grid-wide stride (envs are independent, no inter-warp communication after the staging).
+__global__ void k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
+                      int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* img = smem + 4;  // 16 B after the barrier
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t bytes = (uint32_t)dm.image_words * 4u;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(img, image, bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
+  float* probe = scratch + dm.env_words;
+  Ctx c{&dm, img, scratch, lane};
+  for (int env = blockIdx.x * warps + warp; env < num_envs; env += gridDim.x * warps) {
+    run_env(c, B, env, mode, skip_frames, mask, probe);
+    __syncwarp();
+  }
+}
+
+}  // namespace mjb
+
+struct mjb_batch {
+  mjb::DevImage img;
+  mjb_buffers B;
+  int num_envs = 0, device = 0, warps = 0, grid = 0;
+  size_t smem_bytes = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t* d_image = nullptr;
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  // pinned staging for the host-buffer entry point
+  float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
+  uint8_t *h_term = nullptr, *h_trunc = nullptr;
+};
+
+namespace {
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      mjb::set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                   \
+      return MJB_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (b->timing) {
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, b->stream));
+  }
+  mjb::k_env<<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode,
+                                                                     skip_frames, mask);
+  CUDA_TRY(cudaGetLastError());
+  if (b->timing) {
+    CUDA_TRY(cudaEventRecord(e1, b->stream));
+    b->events.emplace_back(e0, e1);
+  }
+  b->launches++;
+  return MJB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+uint32_t mjb_draw_u32(uint64_t seed, uint32_t env, uint32_t agent, uint32_t counter) {
+  return mjb::draw_u32(seed, env, agent, counter);
+}
+
+int mjb_batch_layout(const mjb_model* m, const mjb_env_spec* spec, int32_t num_envs, mjb_layout* out) {
+  if (!m || !spec || !out || num_envs < 1) { mjb::set_error("mjb_batch_layout: bad argument"); return MJB_ERR_ARG; }
+  try {
+    mjb::ModelView mv(m->host.blob.data());
+    mjb::DevImage img;
+    mjb::build_dev_model(mv, *spec, img);
+    mjb::fill_layout(img.dm, num_envs, *out);
+    return MJB_OK;
+  } catch (const std::exception& e) {
+    mjb::set_error(e.what());
+    return MJB_ERR_LIMIT;
+  }
+}
+
+int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_envs, int32_t device, void* stream,
+                     const mjb_buffers* buffers, mjb_batch** out) {
+  if (!m || !spec || !buffers || !out || num_envs < 1) { mjb::set_error("mjb_batch_create: bad argument"); return MJB_ERR_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    mjb::set_error("mjb_batch_create: no CUDA device (the step path has no CPU fallback)");
+    return MJB_ERR_CUDA;
+  }
+  mjb_batch* b = new mjb_batch();
+  try {
+    mjb::ModelView mv(m->host.blob.data());
+    mjb::build_dev_model(mv, *spec, b->img);
+  } catch (const std::exception& e) {
+    mjb::set_error(e.what());
+    delete b;
+    return MJB_ERR_LIMIT;
+  }
+  b->B = *buffers;
+  b->num_envs = num_envs; b->device = device; b->stream = (cudaStream_t)stream;
+  const mjb::DevModel& dm = b->img.dm;
+  for (const void* p : {(const void*)b->B.qpos, (const void*)b->B.qvel, (const void*)b->B.ctrl, (const void*)b->B.warmstart,
+                        (const void*)b->B.sensordata, (const void*)b->B.probe, (const void*)b->B.actions, (const void*)b->B.obs,
+                        (const void*)b->B.reward, (const void*)b->B.term, (const void*)b->B.trunc, (const void*)b->B.timestep,
+                        (const void*)b->B.store_i, (const void*)b->B.store_f})
+    if (!p) { mjb::set_error("mjb_batch_create: a required buffer is NULL"); delete b; return MJB_ERR_ARG; }
+  auto fail = [&](int rc) { mjb_batch_destroy(b); return rc; };
+  if (cudaSetDevice(device) != cudaSuccess) { mjb::set_error("cudaSetDevice failed"); return fail(MJB_ERR_CUDA); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { mjb::set_error("cudaGetDeviceProperties failed"); return fail(MJB_ERR_CUDA); }
+  size_t max_smem = prop.sharedMemPerBlockOptin;
+  size_t fixed = 16 + (size_t)dm.image_words * 4;
+  size_t per_env = ((size_t)dm.env_words + 4 * ((dm.nprobe + 3) & ~3)) * 4;
+  int warps = (int)((max_smem - fixed) / per_env);
+  int cap = mjb::env_int("MJB_WARPS", 16);
+  if (warps > cap) warps = cap;
+  if (warps < 1) { mjb::set_error("model needs more shared memory per environment than one SM has"); return fail(MJB_ERR_LIMIT); }
+  // even out the rounds: the fewest warps per CTA that keeps the same number of passes over the envs
+  int sms = prop.multiProcessorCount;
+  int rounds = (num_envs + sms * warps - 1) / (sms * warps);
+  int even = (num_envs + sms * rounds - 1) / (sms * rounds);
+  if (even < warps) warps = even < 1 ? 1 : even;
+  b->warps = warps;
+  b->grid = (num_envs + warps - 1) / warps;
+  if (b->grid > sms) b->grid = sms;
+  b->smem_bytes = fixed + per_env * warps;
+  if (cudaFuncSetAttribute(mjb::k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes) != cudaSuccess) {
+    mjb::set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return fail(MJB_ERR_CUDA);
+  }
+  if (cudaMalloc(&b->d_image, (size_t)dm.image_words * 4) != cudaSuccess ||
+      cudaMemcpy(b->d_image, b->img.words.data(), (size_t)dm.image_words * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    mjb::set_error("device image upload failed");
+    return fail(MJB_ERR_CUDA);
+  }
+  const int A = dm.n_agents;
+  if (cudaMallocHost(&b->h_act, sizeof(float) * (size_t)num_envs * A * dm.act_stride + 16) != cudaSuccess ||
+      cudaMallocHost(&b->h_obs, sizeof(float) * (size_t)num_envs * A * dm.obs_stride + 16) != cudaSuccess ||
+      cudaMallocHost(&b->h_rew, sizeof(float) * (size_t)num_envs * A + 16) != cudaSuccess ||
+      cudaMallocHost(&b->h_term, (size_t)num_envs * (A + 1) + 16) != cudaSuccess ||
+      cudaMallocHost(&b->h_trunc, (size_t)num_envs * (A + 1) + 16) != cudaSuccess) {
+    mjb::set_error("pinned staging allocation failed");
+    return fail(MJB_ERR_CUDA);
+  }
+  *out = b;
+  return MJB_OK;
+}
+
+void mjb_batch_destroy(mjb_batch* b) {
+  if (!b) return;
+  for (auto& ev : b->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (b->d_image) cudaFree(b->d_image);
+  if (b->h_act) cudaFreeHost(b->h_act);
+  if (b->h_obs) cudaFreeHost(b->h_obs);
+  if (b->h_rew) cudaFreeHost(b->h_rew);
+  if (b->h_term) cudaFreeHost(b->h_term);
+  if (b->h_trunc) cudaFreeHost(b->h_trunc);
+  delete b;
+}
+
+int mjb_reset(mjb_batch* b, const uint8_t* mask_dev) {
+  if (!b) { mjb::set_error("mjb_reset: null batch"); return MJB_ERR_ARG; }
+  return launch(b, mjb::MODE_RESET, 0, mask_dev);
+}
+int mjb_step(mjb_batch* b) {
+  if (!b) { mjb::set_error("mjb_step: null batch"); return MJB_ERR_ARG; }
+  return launch(b, mjb::MODE_STEP, b->img.dm.skip_frames, nullptr);
+}
+int mjb_physics(mjb_batch* b, int32_t skip_frames) {
+  if (!b || skip_frames < 0) { mjb::set_error("mjb_physics: bad argument"); return MJB_ERR_ARG; }
+  return launch(b, mjb::MODE_PHYSICS, skip_frames, nullptr);
+}
+int mjb_forward(mjb_batch* b) {
+  if (!b) { mjb::set_error("mjb_forward: null batch"); return MJB_ERR_ARG; }
+  return launch(b, mjb::MODE_FORWARD, 0, nullptr);
+}
+int mjb_sync(mjb_batch* b) {
+  if (!b) { mjb::set_error("mjb_sync: null batch"); return MJB_ERR_ARG; }
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return MJB_OK;
+}
+
+int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward, uint8_t* term, uint8_t* trunc) {
+  if (!b || !actions || !obs || !reward || !term || !trunc) { mjb::set_error("mjb_step_host: null argument"); return MJB_ERR_ARG; }
+  const mjb::DevModel& dm = b->img.dm;
+  const size_t N = b->num_envs, A = dm.n_agents;
+  const size_t nb_act = sizeof(float) * N * A * dm.act_stride, nb_obs = sizeof(float) * N * A * dm.obs_stride;
+  const size_t nb_rew = sizeof(float) * N * A, nb_flag = N * (A + 1);
+  memcpy(b->h_act, actions, nb_act);
+  CUDA_TRY(cudaMemcpyAsync(b->B.actions, b->h_act, nb_act, cudaMemcpyHostToDevice, b->stream));
+  int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr);
+  if (rc != MJB_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(b->h_obs, b->B.obs, nb_obs, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(b->h_rew, b->B.reward, nb_rew, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(b->h_term, b->B.term, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(b->h_trunc, b->B.trunc, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  memcpy(obs, b->h_obs, nb_obs);
+  memcpy(reward, b->h_rew, nb_rew);
+  memcpy(term, b->h_term, nb_flag);
+  memcpy(trunc, b->h_trunc, nb_flag);
+  return MJB_OK;
+}
+
+int64_t mjb_launch_count(const mjb_batch* b) { return b ? b->launches : 0; }
+
+int mjb_set_timing(mjb_batch* b, int32_t enable) {
+  if (!b) { mjb::set_error("mjb_set_timing: null batch"); return MJB_ERR_ARG; }
+  b->timing = enable != 0;
+  return MJB_OK;
+}
+
+int mjb_kernel_time_ms(mjb_batch* b, double* total_ms, int64_t* launches) {
+  if (!b || !total_ms || !launches) { mjb::set_error("mjb_kernel_time_ms: null argument"); return MJB_ERR_ARG; }
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  double tot = 0;
+  for (auto& ev : b->events) {
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    tot += ms;
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  *total_ms = tot; *launches = (int64_t)b->events.size();
+  b->events.clear();
+  return MJB_OK;
+}
+
+/* query of the launch geometry, for bench / docs */
+int mjb_batch_geometry(const mjb_batch* b, int32_t* grid, int32_t* warps_per_cta, int64_t* smem_bytes) {
+  if (!b) return MJB_ERR_ARG;
+  if (grid) *grid = b->grid;
+  if (warps_per_cta) *warps_per_cta = b->warps;
+  if (smem_bytes) *smem_bytes = (int64_t)b->smem_bytes;
+  return MJB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1083 @@
+// step_kernel.cuh — one warp = one environment: the batched MuJoCoRL.step hot path.
+//
+// Replaces, per environment (paths relative to the reference repo):
+//   apply_action + skip_frames x mj.mj_step      MuJoCo_Gym/mujoco_parent.py:316-336
+//   get_observations                             MuJoCo_Gym/mujoco_parent.py:380-392
+//   dynamics / reward / truncation / done loops  MuJoCo_Gym/mujoco_rl.py:215-241,262-288,406-417
+//   reset                                        MuJoCo_Gym/mujoco_rl.py:291-331, mujoco_parent.py:341-358
+// The physics restates MuJoCo's documented forward-dynamics pipeline for the MJCF subset in use
+// (kinematics, composite inertia, RNE bias, primitive collisions, soft limit + pyramidal contact
+// constraints, primal Newton solve, semi-implicit Euler with implicit joint damping / RK4, sensors).
+//
+// Mapping: lane = body / dof / geom / collision pair / constraint row depending on the phase, all
+// scratch in shared memory, model constants in shared memory (staged by TMA bulk copy), fp32.
+// The file is plain C++ over the primitives in warp_prims.cuh so that it also compiles for the host
+// SIMT emulator in tests/emu (debug tooling only).
+#pragma once
+#include "../../include/mjb.h"
+#include "dev_model.h"
+#include "warp_prims.cuh"
+
+namespace mjb {
+
+#define MJB_MINVAL 1e-15f
+#define MJB_BIG 1e30f
+
+struct f3 { float x, y, z; };
+struct q4 { float w, x, y, z; };
+MJB_DEV f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+MJB_DEV f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+MJB_DEV f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+MJB_DEV f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+MJB_DEV float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+MJB_DEV f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+MJB_DEV f3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+MJB_DEV void st3(float* p, f3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+MJB_DEV float comp(f3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+MJB_DEV q4 ldq(const float* p) { q4 q; q.w = p[0]; q.x = p[1]; q.y = p[2]; q.z = p[3]; return q; }
+MJB_DEV q4 qmul(q4 a, q4 b) {
+  q4 r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+  r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+  return r;
+}
+MJB_DEV q4 qnorm(q4 q) {
+  float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+  if (n2 < 1e-30f) { q.w = 1; q.x = q.y = q.z = 0; return q; }
+  float inv = 1.0f / sqrtf(n2);
+  q.w *= inv; q.x *= inv; q.y *= inv; q.z *= inv;
+  return q;
+}
+MJB_DEV void q2m(q4 q, float* m) {
+  float ww = q.w * q.w, xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z;
+  m[0] = ww + xx - yy - zz; m[4] = ww - xx + yy - zz; m[8] = ww - xx - yy + zz;
+  m[1] = 2 * (q.x * q.y - q.w * q.z); m[2] = 2 * (q.x * q.z + q.w * q.y);
+  m[3] = 2 * (q.x * q.y + q.w * q.z); m[5] = 2 * (q.y * q.z - q.w * q.x);
+  m[6] = 2 * (q.x * q.z - q.w * q.y); m[7] = 2 * (q.y * q.z + q.w * q.x);
+}
+MJB_DEV f3 mulv(const float* m, f3 v) {
+  return mk3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
+MJB_DEV f3 mulTv(const float* m, f3 v) {
+  return mk3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z);
+}
+MJB_DEV f3 colv(const float* m, int c) { return mk3(m[c], m[3 + c], m[6 + c]); }
+MJB_DEV f3 qrot(q4 q, f3 v) {
+  // v + 2 w (u x v) + 2 u x (u x v)
+  f3 u = mk3(q.x, q.y, q.z);
+  f3 t = cross(u, v) * 2.0f;
+  return v + t * q.w + cross(u, t);
+}
+MJB_DEV q4 axisangle(f3 ax, float ang) {
+  float s, c;
+  sincosf(0.5f * ang, &s, &c);
+  q4 q; q.w = c; q.x = ax.x * s; q.y = ax.y * s; q.z = ax.z * s;
+  return q;
+}
+
+// ---- kernel context ----------------------------------------------------------------------------
+struct Ctx {
+  const DevModel* dm;
+  const uint32_t* img;  // constant image (shared memory)
+  float* s;             // this env's scratch (shared memory)
+  int lane;
+};
+#define CI(f) ((const int*)(c.img + c.dm->off[IF_##f]))
+#define CU(f) ((const uint32_t*)(c.img + c.dm->off[IF_##f]))
+#define CF(f) ((const float*)(c.img + c.dm->off[IF_##f]))
+#define SF(f) (c.s + c.dm->soff[SF_##f])
+#define SI(f) ((int*)(c.s + c.dm->soff[SF_##f]))
+
+// spatial helpers: motion [w; v], force [n; f], inertia {m, h(3), I(6: xx yy zz xy xz yz)} about o
+MJB_DEV void inertia_mul(const float* I, f3 w, f3 v, f3& n, f3& f) {
+  f3 h = mk3(I[1], I[2], I[3]);
+  f = v * I[0] + cross(w, h);
+  f3 Iw = mk3(I[4] * w.x + I[7] * w.y + I[8] * w.z, I[7] * w.x + I[5] * w.y + I[9] * w.z, I[8] * w.x + I[9] * w.y + I[6] * w.z);
+  n = Iw + cross(h, v);
+}
+
+// =================================================================================================
+// kinematics: body frames, motion subspaces (about the tree root's origin), inertias, geom frames
+MJB_DEV void fk(const Ctx& c) {
+  const DevModel& dm = *c.dm;
+  const int* level_adr = CI(level_adr);
+  float* qpos = SF(qpos);
+  float *xpos = SF(xpos), *xquat = SF(xquat), *xmat = SF(xmat), *xipos = SF(xipos), *cdof = SF(cdof);
+  for (int l = 0; l < dm.nlevel; l++) {
+    for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
+      int p = CI(mb_parent)[b], root = CI(mb_root)[b];
+      f3 pos = ld3(CF(mb_pos) + 3 * b);
+      q4 quat = ldq(CF(mb_quat) + 4 * b);
+      if (p >= 0) {
+        pos = ld3(xpos + 3 * p) + mulv(xmat + 9 * p, pos);
+        quat = qmul(ldq(xquat + 4 * p), quat);
+      }
+      int ja = CI(mb_jntadr)[b], jn = CI(mb_jntnum)[b];
+      for (int j = ja; j < ja + jn; j++) {
+        int type = CI(jnt_type)[j], qa = CI(jnt_qposadr)[j], da = CI(jnt_dofadr)[j];
+        if (type == MJB_JNT_FREE) {
+          pos = ld3(qpos + qa);
+          quat = qnorm(ldq(qpos + qa + 3));
+          qpos[qa + 3] = quat.w; qpos[qa + 4] = quat.x; qpos[qa + 5] = quat.y; qpos[qa + 6] = quat.z;
+        } else {
+          f3 jpos = ld3(CF(jnt_pos) + 3 * j), jax = ld3(CF(jnt_axis) + 3 * j);
+          f3 anchor = pos + qrot(quat, jpos), axis = qrot(quat, jax);
+          float q = qpos[qa] - CF(jnt_qpos0)[j];
+          // stash [axis; anchor] now, converted to a motion vector once the tree origin is known
+          st3(cdof + 6 * da, axis); st3(cdof + 6 * da + 3, anchor);
+          if (type == MJB_JNT_HINGE) {
+            quat = qmul(quat, axisangle(jax, q));
+            pos = anchor - qrot(quat, jpos);
+          } else {
+            pos = pos + axis * q;
+          }
+        }
+      }
+      quat = qnorm(quat);
+      float R[9];
+      q2m(quat, R);
+      st3(xpos + 3 * b, pos);
+      xquat[4 * b] = quat.w; xquat[4 * b + 1] = quat.x; xquat[4 * b + 2] = quat.y; xquat[4 * b + 3] = quat.z;
+#pragma unroll
+      for (int i = 0; i < 9; i++) xmat[9 * b + i] = R[i];
+      st3(xipos + 3 * b, pos + mulv(R, ld3(CF(mb_ipos) + 3 * b)));
+      f3 o = (root == b) ? pos : ld3(xpos + 3 * root);
+      for (int j = ja; j < ja + jn; j++) {
+        int type = CI(jnt_type)[j], da = CI(jnt_dofadr)[j];
+        if (type == MJB_JNT_FREE) {
+          for (int i = 0; i < 3; i++) {
+            st3(cdof + 6 * (da + i), mk3(0, 0, 0));
+            st3(cdof + 6 * (da + i) + 3, mk3(i == 0, i == 1, i == 2));
+            f3 ax = colv(R, i);
+            st3(cdof + 6 * (da + 3 + i), ax);
+            st3(cdof + 6 * (da + 3 + i) + 3, cross(ax, o - pos));
+          }
+        } else if (type == MJB_JNT_HINGE) {
+          f3 axis = ld3(cdof + 6 * da), anchor = ld3(cdof + 6 * da + 3);
+          st3(cdof + 6 * da + 3, cross(axis, o - anchor));
+        } else {
+          f3 axis = ld3(cdof + 6 * da);
+          st3(cdof + 6 * da, mk3(0, 0, 0)); st3(cdof + 6 * da + 3, axis);
+        }
+      }
+    }
+    MJB_SYNC();
+  }
+  // body inertias about the tree origin
+  float* cinert = SF(cinert);
+  for (int b = c.lane; b < dm.nmb; b += 32) {
+    float R[9];
+    q2m(qmul(ldq(xquat + 4 * b), ldq(CF(mb_iquat) + 4 * b)), R);
+    f3 I = ld3(CF(mb_inertia) + 3 * b);
+    float m = CF(mb_mass)[b];
+    f3 cc = ld3(xipos + 3 * b) - ld3(xpos + 3 * CI(mb_root)[b]);
+    float* o = cinert + 10 * b;
+    o[0] = m; o[1] = m * cc.x; o[2] = m * cc.y; o[3] = m * cc.z;
+    o[4] = R[0] * R[0] * I.x + R[1] * R[1] * I.y + R[2] * R[2] * I.z + m * (cc.y * cc.y + cc.z * cc.z);
+    o[5] = R[3] * R[3] * I.x + R[4] * R[4] * I.y + R[5] * R[5] * I.z + m * (cc.x * cc.x + cc.z * cc.z);
+    o[6] = R[6] * R[6] * I.x + R[7] * R[7] * I.y + R[8] * R[8] * I.z + m * (cc.x * cc.x + cc.y * cc.y);
+    o[7] = R[0] * R[3] * I.x + R[1] * R[4] * I.y + R[2] * R[5] * I.z - m * cc.x * cc.y;
+    o[8] = R[0] * R[6] * I.x + R[1] * R[7] * I.y + R[2] * R[8] * I.z - m * cc.x * cc.z;
+    o[9] = R[3] * R[6] * I.x + R[4] * R[7] * I.y + R[5] * R[8] * I.z - m * cc.y * cc.z;
+  }
+  // dynamic geom frames
+  float *gpos = SF(gpos), *gmat = SF(gmat);
+  for (int g = c.lane; g < dm.ngeom; g += 32) {
+    int slot = CI(geom_slot)[g];
+    if (slot < 0) continue;
+    int b = CI(geom_mb)[g];
+    st3(gpos + 3 * slot, ld3(xpos + 3 * b) + mulv(xmat + 9 * b, ld3(CF(geom_pos) + 3 * g)));
+    q2m(qmul(ldq(xquat + 4 * b), ldq(CF(geom_quat) + 4 * g)), gmat + 9 * slot);
+  }
+  float *spos = SF(spos), *smat = SF(smat);
+  for (int t = c.lane; t < dm.nsite; t += 32) {
+    int b = CI(site_mb)[t];
+    f3 lp = ld3(CF(site_pos) + 3 * t);
+    q4 lq = ldq(CF(site_quat) + 4 * t);
+    if (b >= 0) { lp = ld3(xpos + 3 * b) + mulv(xmat + 9 * b, lp); lq = qmul(ldq(xquat + 4 * b), lq); }
+    st3(spos + 3 * t, lp);
+    q2m(lq, smat + 9 * t);
+  }
+  MJB_SYNC();
+}
+
+// composite rigid body inertias and the joint-space inertia matrix (dense, ld = dm.ldm)
+MJB_DEV void crb_mass(const Ctx& c) {
+  const DevModel& dm = *c.dm;
+  const int* level_adr = CI(level_adr);
+  float *cinert = SF(cinert), *crb = SF(crb), *M = SF(M), *cdof = SF(cdof);
+  for (int i = c.lane; i < 10 * dm.nmb; i += 32) crb[i] = cinert[i];
+  for (int i = c.lane; i < dm.nv * dm.ldm; i += 32) M[i] = 0.f;
+  MJB_SYNC();
+  for (int l = dm.nlevel - 2; l >= 0; l--) {
+    for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
+      int ca = CI(mb_childadr)[b], ce = CI(mb_childadr)[b + 1];
+      if (ce > ca) {
+        float acc[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) acc[i] = crb[10 * b + i];
+        for (int k = ca; k < ce; k++) {
+          int ch = CI(mb_child)[k];
+#pragma unroll
+          for (int i = 0; i < 10; i++) acc[i] += crb[10 * ch + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) crb[10 * b + i] = acc[i];
+      }
+    }
+    MJB_SYNC();
+  }
+  for (int i = c.lane; i < dm.nv; i += 32) {
+    int b = CI(dof_mb)[i];
+    f3 n, f;
+    inertia_mul(crb + 10 * b, ld3(cdof + 6 * i), ld3(cdof + 6 * i + 3), n, f);
+    for (int j = i; j >= 0; j = CI(dof_parent)[j]) {
+      float v = dot(ld3(cdof + 6 * j), n) + dot(ld3(cdof + 6 * j + 3), f);
+      if (j == i) v += CF(dof_armature)[i];
+      M[i * dm.ldm + j] = v;
+      M[j * dm.ldm + i] = v;
+    }
+  }
+  MJB_SYNC();
+}
+
+// velocity-dependent bias forces (Coriolis, centrifugal, gravity) by recursive Newton-Euler, then
+// qfrc_smooth = passive - bias + actuation.  With `with_acc` the pass includes qacc (post-constraint
+// body accelerations for the accelerometer) and only fills cvel / cacc.
+MJB_DEV void rne_pass(const Ctx& c, bool with_acc) {
+  const DevModel& dm = *c.dm;
+  const int* level_adr = CI(level_adr);
+  float *cdof = SF(cdof), *cvel = SF(cvel), *cacc = SF(cacc), *qvel = SF(qvel), *qacc = SF(qacc);
+  float *cinert = SF(cinert), *cfrc = SF(crb);  // crb is dead after crb_mass: reuse as body force
+  for (int l = 0; l < dm.nlevel; l++) {
+    for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
+      int p = CI(mb_parent)[b];
+      f3 w = mk3(0, 0, 0), v = mk3(0, 0, 0), aw = mk3(0, 0, 0);
+      f3 av = mk3(-dm.gravity[0], -dm.gravity[1], -dm.gravity[2]);
+      if (p >= 0) { w = ld3(cvel + 6 * p); v = ld3(cvel + 6 * p + 3); aw = ld3(cacc + 6 * p); av = ld3(cacc + 6 * p + 3); }
+      int da = CI(mb_dofadr)[b], dn = CI(mb_dofnum)[b];
+      f3 wb = w, vb = v;  // velocity snapshot for the free joint's rotational block
+      for (int d = da; d < da + dn; d++) {
+        int kind = CI(dof_kind)[d];
+        f3 sw = ld3(cdof + 6 * d), sv = ld3(cdof + 6 * d + 3);
+        float qd = qvel[d];
+        if (kind == DOF_FREE_ROT && d == da + 3) { wb = w; vb = v; }
+        if (kind != DOF_FREE_TRANS) {
+          f3 uw = kind == DOF_FREE_ROT ? wb : w, uv = kind == DOF_FREE_ROT ? vb : v;
+          // cdof_dot = u x_m S
+          aw = aw + cross(uw, sw) * qd;
+          av = av + (cross(uw, sv) + cross(uv, sw)) * qd;
+        }
+        if (with_acc) { aw = aw + sw * qacc[d]; av = av + sv * qacc[d]; }
+        w = w + sw * qd; v = v + sv * qd;
+      }
+      st3(cvel + 6 * b, w); st3(cvel + 6 * b + 3, v);
+      st3(cacc + 6 * b, aw); st3(cacc + 6 * b + 3, av);
+      if (!with_acc) {
+        f3 n1, f1, n2, f2;
+        inertia_mul(cinert + 10 * b, aw, av, n1, f1);
+        inertia_mul(cinert + 10 * b, w, v, n2, f2);
+        // v x* (I v) = [w x n + v x f ; w x f]
+        st3(cfrc + 10 * b, n1 + cross(w, n2) + cross(v, f2));
+        st3(cfrc + 10 * b + 3, f1 + cross(w, f2));
+      }
+    }
+    MJB_SYNC();
+  }
+  if (with_acc) return;
+  for (int l = dm.nlevel - 2; l >= 0; l--) {
+    for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
+      int ca = CI(mb_childadr)[b], ce = CI(mb_childadr)[b + 1];
+      for (int k = ca; k < ce; k++) {
+        int ch = CI(mb_child)[k];
+#pragma unroll
+        for (int i = 0; i < 6; i++) cfrc[10 * b + i] += cfrc[10 * ch + i];
+      }
+    }
+    MJB_SYNC();
+  }
+  float *qfrc = SF(qfrc), *ctrl = SF(ctrl);
+  for (int d = c.lane; d < dm.nv; d += 32) {
+    int b = CI(dof_mb)[d];
+    float bias = dot(ld3(cdof + 6 * d), ld3(cfrc + 10 * b)) + dot(ld3(cdof + 6 * d + 3), ld3(cfrc + 10 * b + 3));
+    float f = -CF(dof_damping)[d] * qvel[d] - bias;
+    for (int u = 0; u < dm.nu; u++)
+      if (CI(act_dof)[u] == d) {
+        const float* ap = CF(act_param) + 4 * u;
+        float cv = ctrl[u];
+        if (ap[1] != 0.f) cv = fminf(ap[3], fmaxf(ap[2], cv));
+        f += ap[0] * cv;
+      }
+    qfrc[d] = f;
+  }
+  MJB_SYNC();
+}
+
+// =================================================================================================
+// collision
+struct GeomW { f3 pos; const float* mat; const float* size; int type; };
+MJB_DEV GeomW geom_world(const Ctx& c, int g) {
+  GeomW r;
+  int slot = CI(geom_slot)[g];
+  r.type = CI(geom_type)[g];
+  r.size = CF(geom_size) + 3 * g;
+  if (slot >= 0) { r.pos = ld3(SF(gpos) + 3 * slot); r.mat = SF(gmat) + 9 * slot; }
+  else { r.pos = ld3(CF(geom_pos) + 3 * g); r.mat = CF(geom_mat) + 9 * g; }
+  return r;
+}
+struct ConOut { float dist; f3 pos, n, t; };
+
+MJB_DEV int plane_sphere(f3 pp, f3 n, f3 cs, float r, float margin, ConOut& o) {
+  float dist = dot(cs - pp, n) - r;
+  if (dist > margin) return 0;
+  o.dist = dist; o.pos = cs - n * (r + 0.5f * dist); o.n = n; o.t = mk3(0, 0, 0);
+  return 1;
+}
+MJB_DEV int sphere_sphere(f3 c1, float r1, f3 c2, float r2, float margin, ConOut& o) {
+  f3 d = c2 - c1;
+  float cd = sqrtf(dot(d, d)), dist = cd - r1 - r2;
+  if (dist > margin) return 0;
+  f3 n = cd < MJB_MINVAL ? mk3(1, 0, 0) : d * (1.0f / cd);
+  o.dist = dist; o.pos = c1 + n * (r1 + 0.5f * dist); o.n = n; o.t = mk3(0, 0, 0);
+  return 1;
+}
+MJB_DEV int sphere_box(f3 c1, float r, f3 c2, const float* R2, const float* size, float margin, ConOut& o) {
+  f3 cl = mulTv(R2, c1 - c2);
+  f3 cp = mk3(fminf(size[0], fmaxf(-size[0], cl.x)), fminf(size[1], fmaxf(-size[1], cl.y)), fminf(size[2], fmaxf(-size[2], cl.z)));
+  bool inside = (cp.x == cl.x) && (cp.y == cl.y) && (cp.z == cl.z);
+  f3 nl = mk3(0, 0, 0);
+  float dist;
+  if (inside) {
+    float px = size[0] - fabsf(cl.x), py = size[1] - fabsf(cl.y), pz = size[2] - fabsf(cl.z);
+    int k = 0; float best = px;
+    if (py < best) { best = py; k = 1; }
+    if (pz < best) { best = pz; k = 2; }
+    float sg = comp(cl, k) >= 0 ? 1.f : -1.f;
+    if (k == 0) nl.x = -sg; else if (k == 1) nl.y = -sg; else nl.z = -sg;
+    dist = -best - r;
+  } else {
+    f3 d = cl - cp;
+    float len = sqrtf(dot(d, d));
+    dist = len - r;
+    if (dist > margin) return 0;
+    nl = d * (-1.0f / len);
+  }
+  f3 n = mulv(R2, nl);
+  o.dist = dist; o.pos = c1 + n * (r + 0.5f * dist); o.n = n; o.t = mk3(0, 0, 0);
+  return 1;
+}
+MJB_DEV float point_box_dist(f3 p, const float* size) {
+  float ex = fabsf(p.x) - size[0], ey = fabsf(p.y) - size[1], ez = fabsf(p.z) - size[2];
+  float s2 = (ex > 0 ? ex * ex : 0.f) + (ey > 0 ? ey * ey : 0.f) + (ez > 0 ? ez * ez : 0.f);
+  return s2 > 0 ? sqrtf(s2) : fmaxf(ex, fmaxf(ey, ez));
+}
+MJB_DEV int capsule_box(const GeomW& g1, const GeomW& g2, float margin, ConOut* o) {
+  float r = g1.size[0], h = g1.size[1];
+  f3 ax = colv(g1.mat, 2);
+  f3 a = mulTv(g2.mat, g1.pos - ax * h - g2.pos), b = mulTv(g2.mat, g1.pos + ax * h - g2.pos);
+  f3 ab = b - a;
+  float lo = 0.f, hi = 1.f;
+  const float gr = 0.6180339887f;
+  float x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
+  float f1 = point_box_dist(a + ab * x1, g2.size), f2 = point_box_dist(a + ab * x2, g2.size);
+  for (int it = 0; it < 40; it++) {
+    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = point_box_dist(a + ab * x1, g2.size); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = point_box_dist(a + ab * x2, g2.size); }
+  }
+  float tm = 0.5f * (lo + hi), dmid = point_box_dist(a + ab * tm, g2.size);
+  float d0 = point_box_dist(a, g2.size), d1 = point_box_dist(b, g2.size);
+  int n = 0;
+  if (fminf(d0, d1) <= dmid + 1e-6f) {
+    float t0 = d1 < d0 ? 1.f : 0.f;
+    n += sphere_box(g1.pos + ax * ((2 * t0 - 1) * h), r, g2.pos, g2.mat, g2.size, margin, o[n]);
+    n += sphere_box(g1.pos + ax * ((1 - 2 * t0) * h), r, g2.pos, g2.mat, g2.size, margin, o[n]);
+  } else {
+    n += sphere_box(g1.pos + ax * ((2 * tm - 1) * h), r, g2.pos, g2.mat, g2.size, margin, o[n]);
+  }
+  return n;
+}
+MJB_DEV int capsule_capsule(const GeomW& g1, const GeomW& g2, float margin, ConOut* o) {
+  f3 a1 = colv(g1.mat, 2), a2 = colv(g2.mat, 2), dif = g1.pos - g2.pos;
+  float len1 = g1.size[1], len2 = g2.size[1], r1 = g1.size[0], r2 = g2.size[0];
+  float mb = -dot(a1, a2), u = -dot(a1, dif), v = dot(a2, dif), det = 1.f - mb * mb;
+  if (fabsf(det) >= 1e-7f) {
+    float x1 = (u - mb * v) / det, x2 = (v - mb * u) / det;
+    if (x1 > len1) { x1 = len1; x2 = v - mb * len1; }
+    else if (x1 < -len1) { x1 = -len1; x2 = v + mb * len1; }
+    if (x2 > len2) { x2 = len2; x1 = u - mb * len2; }
+    else if (x2 < -len2) { x2 = -len2; x1 = u + mb * len2; }
+    x1 = fminf(len1, fmaxf(-len1, x1));
+    return sphere_sphere(g1.pos + a1 * x1, r1, g2.pos + a2 * x2, r2, margin, o[0]);
+  }
+  int k = 0;
+  for (int e = 0; e < 2 && k < 2; e++) {
+    float x1 = e == 0 ? len1 : -len1, x2 = fminf(len2, fmaxf(-len2, v - mb * x1));
+    k += sphere_sphere(g1.pos + a1 * x1, r1, g2.pos + a2 * x2, r2, margin, o[k]);
+  }
+  for (int e = 0; e < 2 && k < 2; e++) {
+    float x2 = e == 0 ? len2 : -len2, x1 = u - mb * x2;
+    if (x1 > len1 || x1 < -len1) continue;
+    k += sphere_sphere(g1.pos + a1 * x1, r1, g2.pos + a2 * x2, r2, margin, o[k]);
+  }
+  return k;
+}
+
+MJB_DEV void make_frame(f3 n, f3 t, float* fr) {
+  float nn = sqrtf(dot(n, n));
+  n = n * (1.0f / nn);
+  if (dot(t, t) < 0.25f) {
+    t = mk3(0, 0, 0);
+    if (n.y < 0.5f && n.y > -0.5f) t.y = 1; else t.z = 1;
+  }
+  t = t - n * dot(n, t);
+  t = t * (1.0f / sqrtf(dot(t, t)));
+  st3(fr, n); st3(fr + 3, t); st3(fr + 6, cross(n, t));
+}
+
+// append one contact record; `idx` already bounds-checked
+MJB_DEV void store_contact(const Ctx& c, int idx, const ConOut& o, int pair, float mu) {
+  float* r = SF(con) + CON_STRIDE * idx;
+  r[CON_DIST] = o.dist;
+  st3(r + CON_POS, o.pos);
+  make_frame(o.n, o.t, r + CON_FRAME);
+  ((int*)r)[CON_PAIR] = pair;
+  r[CON_MU] = mu;
+}
+
+// returns the number of contacts (warp-uniform); fills SF_con
+MJB_DEV int collide(const Ctx& c) {
+  const DevModel& dm = *c.dm;
+  const uint32_t* pairs = CU(pair_pack);
+  int* cand = SI(cand);
+  int ncand = 0;
+  // broad phase: bounding spheres (planes: signed distance of the centre)
+  for (int base = 0; base < dm.npair; base += 32) {
+    int p = base + c.lane;
+    bool keep = false;
+    if (p < dm.npair) {
+      uint32_t pk = pairs[p];
+      int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
+      float margin = CF(pclass)[PC_STRIDE * (pk >> 24) + PC_MARGIN];
+      GeomW a = geom_world(c, g1), b = geom_world(c, g2);
+      float rb2 = CF(geom_rbound)[g2];
+      if (a.type == MJB_GEOM_PLANE) keep = dot(b.pos - a.pos, colv(a.mat, 2)) <= rb2 + margin;
+      else {
+        float rr = CF(geom_rbound)[g1] + rb2 + margin;
+        f3 d = b.pos - a.pos;
+        keep = dot(d, d) <= rr * rr;
+      }
+    }
+    uint32_t bal = MJB_BALLOT(keep);
+    int idx = ncand + MJB_POPC(bal & ((1u << c.lane) - 1u));
+    if (keep && idx < dm.maxcand) cand[idx] = p;
+    ncand += MJB_POPC(bal);
+  }
+  if (ncand > dm.maxcand) ncand = dm.maxcand;
+  MJB_SYNC();
+  // narrow phase, lane = candidate (types with at most two contacts)
+  int ncon = 0;
+  for (int base = 0; base < ncand; base += 32) {
+    int i = base + c.lane;
+    int n = 0, p = -1;
+    ConOut o[2];
+    float mu = 0.f;
+    if (i < ncand) {
+      p = cand[i];
+      uint32_t pk = pairs[p];
+      int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
+      const float* pc = CF(pclass) + PC_STRIDE * (pk >> 24);
+      float margin = pc[PC_MARGIN];
+      mu = pc[PC_MU];
+      GeomW a = geom_world(c, g1), b = geom_world(c, g2);
+      if (a.type == MJB_GEOM_PLANE) {
+        f3 nrm = colv(a.mat, 2);
+        if (b.type == MJB_GEOM_SPHERE) n = plane_sphere(a.pos, nrm, b.pos, b.size[0], margin, o[0]);
+        else if (b.type == MJB_GEOM_CAPSULE) {
+          f3 ax = colv(b.mat, 2);
+          n = plane_sphere(a.pos, nrm, b.pos + ax * b.size[1], b.size[0], margin, o[0]);
+          n += plane_sphere(a.pos, nrm, b.pos - ax * b.size[1], b.size[0], margin, o[n]);
+          o[0].t = ax; o[1].t = ax;
+        }
+      } else if (a.type == MJB_GEOM_SPHERE) {
+        if (b.type == MJB_GEOM_SPHERE) n = sphere_sphere(a.pos, a.size[0], b.pos, b.size[0], margin, o[0]);
+        else if (b.type == MJB_GEOM_CAPSULE) {
+          f3 ax = colv(b.mat, 2);
+          float x = fminf(b.size[1], fmaxf(-b.size[1], dot(ax, a.pos - b.pos)));
+          n = sphere_sphere(a.pos, a.size[0], b.pos + ax * x, b.size[0], margin, o[0]);
+        } else if (b.type == MJB_GEOM_BOX) n = sphere_box(a.pos, a.size[0], b.pos, b.mat, b.size, margin, o[0]);
+      } else if (a.type == MJB_GEOM_CAPSULE) {
+        if (b.type == MJB_GEOM_CAPSULE) n = capsule_capsule(a, b, margin, o);
+        else if (b.type == MJB_GEOM_BOX) n = capsule_box(a, b, margin, o);
+      }
+    }
+    for (int k = 0; k < 2; k++) {
+      uint32_t bal = MJB_BALLOT(n > k);
+      int idx = ncon + MJB_POPC(bal & ((1u << c.lane) - 1u));
+      if (n > k && idx < dm.maxcon) store_contact(c, idx, o[k], p, mu);
+      ncon += MJB_POPC(bal);
+    }
+  }
+  // multi-contact types (plane-box, box-box): one candidate at a time, lane = box corner
+  for (int i = 0; i < ncand; i++) {
+    int p = cand[i];
+    uint32_t pk = pairs[p];
+    int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
+    int t1 = CI(geom_type)[g1], t2 = CI(geom_type)[g2];
+    if (t2 != MJB_GEOM_BOX || (t1 != MJB_GEOM_PLANE && t1 != MJB_GEOM_BOX)) continue;  // warp-uniform
+    const float* pc = CF(pclass) + PC_STRIDE * (pk >> 24);
+    float margin = pc[PC_MARGIN], mu = pc[PC_MU];
+    GeomW a = geom_world(c, g1), b = geom_world(c, g2);
+    bool hit = false;
+    ConOut o;
+    o.t = mk3(0, 0, 0);
+    int lim = 4;
+    if (t1 == MJB_GEOM_PLANE) {
+      if (c.lane < 8) {
+        f3 nrm = colv(a.mat, 2);
+        float dist0 = dot(b.pos - a.pos, nrm);
+        f3 vec = mk3(b.size[0] * ((c.lane & 1) ? 1.f : -1.f), b.size[1] * ((c.lane & 2) ? 1.f : -1.f), b.size[2] * ((c.lane & 4) ? 1.f : -1.f));
+        f3 corner = mulv(b.mat, vec);
+        float ld = dot(nrm, corner);
+        if (!(dist0 + ld > margin || ld > 0)) {
+          hit = true; o.dist = dist0 + ld; o.pos = corner + b.pos - nrm * (0.5f * o.dist); o.n = nrm;
+        }
+      }
+    } else {
+      lim = 8;
+      if (c.lane < 16) {
+        int pass = c.lane >> 3, ci = c.lane & 7;
+        const GeomW& A = pass == 0 ? a : b; const GeomW& B = pass == 0 ? b : a;
+        f3 vec = mk3(A.size[0] * ((ci & 1) ? 1.f : -1.f), A.size[1] * ((ci & 2) ? 1.f : -1.f), A.size[2] * ((ci & 4) ? 1.f : -1.f));
+        f3 pw = A.pos + mulv(A.mat, vec);
+        f3 pl = mulTv(B.mat, pw - B.pos);
+        float px = B.size[0] - fabsf(pl.x), py = B.size[1] - fabsf(pl.y), pz = B.size[2] - fabsf(pl.z);
+        if (px >= -margin && py >= -margin && pz >= -margin) {
+          int k = 0; float best = px;
+          if (py < best) { best = py; k = 1; }
+          if (pz < best) { best = pz; k = 2; }
+          f3 nl = mk3(0, 0, 0);
+          float sg = comp(pl, k) >= 0 ? 1.f : -1.f;
+          if (k == 0) nl.x = sg; else if (k == 1) nl.y = sg; else nl.z = sg;
+          f3 nw = mulv(B.mat, nl);
+          hit = true; o.dist = -best; o.pos = pw + nw * (0.5f * best); o.n = pass == 0 ? nw * -1.f : nw;
+        }
+      }
+    }
+    uint32_t bal = MJB_BALLOT(hit);
+    int rank = MJB_POPC(bal & ((1u << c.lane) - 1u));
+    if (hit && rank < lim && ncon + rank < dm.maxcon) store_contact(c, ncon + rank, o, p, mu);
+    int add = MJB_POPC(bal);
+    ncon += add < lim ? add : lim;
+  }
+  if (ncon > dm.maxcon) ncon = dm.maxcon;
+  MJB_SYNC();
+  return ncon;
+}
+
+// =================================================================================================
+// constraints
+MJB_DEV float impedance(const float* solimp, float pos, float margin) {
+  float dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  if (dmin == dmax || width <= MJB_MINVAL) return 0.5f * (dmin + dmax);
+  float x = fabsf((pos - margin) / width);
+  if (x >= 1.f) return dmax;
+  if (x <= 0.f) return dmin;
+  float y;
+  if (power == 1.f) y = x;
+  else if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+  else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
+  else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  return dmin + y * (dmax - dmin);
+}
+
+// rows: [0, 2 nlim) limit slots (lower, upper per limited joint; inactive -> D = 0), then 4 per contact
+MJB_DEV void make_constraints(const Ctx& c, int ncon) {
+  const DevModel& dm = *c.dm;
+  float *efcD = SF(efcD), *efcAref = SF(efcAref), *qpos = SF(qpos), *qvel = SF(qvel);
+  for (int k = c.lane; k < dm.nlim; k += 32) {
+    const float* lp = CF(lim_param) + LIM_STRIDE * k;
+    float q = qpos[CI(lim_qposadr)[k]], v = qvel[CI(lim_dof)[k]];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      float dist = side == 0 ? q - lp[LIM_LO] : lp[LIM_HI] - q;
+      float D = 0.f, aref = 0.f;
+      if (dist < lp[LIM_MARGIN]) {
+        float imp = impedance(lp + LIM_SOLIMP, dist, lp[LIM_MARGIN]);
+        float R = fmaxf(MJB_MINVAL, (1.f - imp) * lp[LIM_INVW] / imp);
+        D = 1.f / R;
+        float vel = side == 0 ? v : -v;
+        aref = -lp[LIM_B] * vel - lp[LIM_K] * imp * (dist - lp[LIM_MARGIN]);
+      }
+      efcD[2 * k + side] = D; efcAref[2 * k + side] = aref;
+    }
+  }
+  // contact Jacobians: lane = dof, rows (normal, tangent1, tangent2) per contact
+  float *J = SF(J), *con = SF(con), *cdof = SF(cdof), *xpos = SF(xpos);
+  const uint32_t* pairs = CU(pair_pack);
+  for (int d = c.lane; d < dm.nv; d += 32) {
+    f3 sw = ld3(cdof + 6 * d), sv = ld3(cdof + 6 * d + 3);
+    int root = CI(mb_root)[CI(dof_mb)[d]];
+    f3 o = ld3(xpos + 3 * root);
+    uint32_t bit = 1u << (d & 31);
+    int word = d >> 5;
+    for (int k = 0; k < ncon; k++) {
+      const float* r = con + CON_STRIDE * k;
+      uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
+      int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
+      int s = 0;
+      if (b2 >= 0 && (CU(mb_dofmask)[2 * b2 + word] & bit)) s += 1;
+      if (b1 >= 0 && (CU(mb_dofmask)[2 * b1 + word] & bit)) s -= 1;
+      float jn = 0.f, jt1 = 0.f, jt2 = 0.f;
+      if (s != 0) {
+        f3 vel = (sv + cross(sw, ld3(r + CON_POS) - o)) * (float)s;
+        jn = dot(ld3(r + CON_FRAME), vel); jt1 = dot(ld3(r + CON_FRAME + 3), vel); jt2 = dot(ld3(r + CON_FRAME + 6), vel);
+      }
+      J[(3 * k) * dm.ldj + d] = jn; J[(3 * k + 1) * dm.ldj + d] = jt1; J[(3 * k + 2) * dm.ldj + d] = jt2;
+    }
+  }
+  MJB_SYNC();
+  // per-contact regulariser and reference acceleration: lane = contact
+  int base = 2 * dm.nlim;
+  for (int k = c.lane; k < ncon; k += 32) {
+    const float* r = con + CON_STRIDE * k;
+    uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
+    const float* pc = CF(pclass) + PC_STRIDE * (pk >> 24);
+    int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
+    float tran = (b1 >= 0 ? CF(mb_invweight)[b1] : 0.f) + (b2 >= 0 ? CF(mb_invweight)[b2] : 0.f);
+    float mu = pc[PC_MU], dist = r[CON_DIST], inc = pc[PC_INCMARGIN];
+    float imp = impedance(pc + PC_SOLIMP, dist, inc);
+    float vn = 0.f, v1 = 0.f, v2 = 0.f;
+    for (int d = 0; d < dm.nv; d++) {
+      float qd = qvel[d];
+      vn += J[(3 * k) * dm.ldj + d] * qd; v1 += J[(3 * k + 1) * dm.ldj + d] * qd; v2 += J[(3 * k + 2) * dm.ldj + d] * qd;
+    }
+    float kpos = pc[PC_K] * imp * (dist - inc), B = pc[PC_B];
+    if (pc[PC_CONDIM] < 2.f) {
+      float R = fmaxf(MJB_MINVAL, (1.f - imp) * tran / imp);
+      efcD[base + 4 * k] = 1.f / R; efcAref[base + 4 * k] = -B * vn - kpos;
+      for (int e = 1; e < 4; e++) { efcD[base + 4 * k + e] = 0.f; efcAref[base + 4 * k + e] = 0.f; }
+    } else {
+      float R0 = fmaxf(MJB_MINVAL, (1.f - imp) * tran * (1.f + mu * mu) / imp);
+      float D = 1.f / (2.f * mu * mu * R0);
+      efcD[base + 4 * k] = D; efcAref[base + 4 * k] = -B * (vn + mu * v1) - kpos;
+      efcD[base + 4 * k + 1] = D; efcAref[base + 4 * k + 1] = -B * (vn - mu * v1) - kpos;
+      efcD[base + 4 * k + 2] = D; efcAref[base + 4 * k + 2] = -B * (vn + mu * v2) - kpos;
+      efcD[base + 4 * k + 3] = D; efcAref[base + 4 * k + 3] = -B * (vn - mu * v2) - kpos;
+    }
+  }
+  MJB_SYNC();
+}
+
+// =================================================================================================
+// dense helpers (nv <= 32: lane = row)
+// out[row] = sum_j A[row][j] x[j]
+MJB_DEV float matvec_row(const float* A, int ld, int n, const float* x, int row) {
+  float s = 0.f;
+  for (int j = 0; j < n; j++) s += A[row * ld + j] * x[j];
+  return s;
+}
+// in-place Cholesky of the lower triangle; lane i owns row i.  Returns 1/L_ii of the lane's row.
+MJB_DEV float cholesky(float* A, int ld, int n, int lane) {
+  float invd = 1.f;
+  for (int j = 0; j < n; j++) {
+    float s = 0.f;
+    if (lane >= j && lane < n) {
+      s = A[lane * ld + j];
+      for (int k = 0; k < j; k++) s -= A[lane * ld + k] * A[j * ld + k];
+    }
+    float sj = MJB_SHFL(s, j);
+    float inv = MJB_RSQRT(fmaxf(sj, 1e-20f));
+    if (lane == j) { invd = inv; A[lane * ld + j] = sj * inv; }
+    else if (lane > j && lane < n) A[lane * ld + j] = s * inv;
+    MJB_SYNC();
+  }
+  return invd;
+}
+// solve L L' x = b with lane-resident b/x
+MJB_DEV float chol_solve(const float* A, int ld, int n, int lane, float invd, float b) {
+  float x = b;
+  for (int k = 0; k < n; k++) {
+    float yk = MJB_SHFL(x * invd, k);
+    if (lane == k) x = yk;
+    else if (lane > k && lane < n) x -= A[lane * ld + k] * yk;
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    float xk = MJB_SHFL(x * invd, k);
+    if (lane == k) x = xk;
+    else if (lane < k) x -= A[k * ld + lane] * xk;
+  }
+  return x;
+}
+
+// jar-like product for every row: out[row] = J_row . x   (limit rows: +-x[dof]; contact rows: pyramid edges)
+MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const float* sub) {
+  const DevModel& dm = *c.dm;
+  for (int k = c.lane; k < dm.nlim; k += 32) {
+    float v = x[CI(lim_dof)[k]];
+    out[2 * k] = v - (sub ? sub[2 * k] : 0.f);
+    out[2 * k + 1] = -v - (sub ? sub[2 * k + 1] : 0.f);
+  }
+  const float* J = SF(J);
+  const float* con = SF(con);
+  int base = 2 * dm.nlim;
+  for (int r = c.lane; r < 3 * ncon; r += 32) {
+    float s = 0.f;
+    for (int d = 0; d < dm.nv; d++) s += J[r * dm.ldj + d] * x[d];
+    out[base + 4 * (r / 3) + (r % 3)] = s;
+  }
+  MJB_SYNC();
+  for (int k = c.lane; k < ncon; k += 32) {
+    float mu = con[CON_STRIDE * k + CON_MU];
+    float n = out[base + 4 * k], t1 = out[base + 4 * k + 1], t2 = out[base + 4 * k + 2];
+    for (int e = 0; e < 4; e++) {
+      float v = n + ((e & 1) ? -mu : mu) * (e < 2 ? t1 : t2);
+      out[base + 4 * k + e] = v - (sub ? sub[base + 4 * k + e] : 0.f);
+    }
+  }
+  MJB_SYNC();
+}
+
+// primal Newton solve for qacc (SF_qacc holds the warm start on entry, the solution on exit).
+// On exit SF_vecA = M qacc, SF_vecB = gradient, SF_efcJar = J qacc - aref.  Returns iterations used.
+MJB_DEV int newton(const Ctx& c, int ncon) {
+  const DevModel& dm = *c.dm;
+  const int nv = dm.nv, lane = c.lane, ldm = dm.ldm;
+  float *M = SF(M), *H = SF(H), *a = SF(qacc), *qfrc = SF(qfrc), *Ma = SF(vecA), *grad = SF(vecB), *sv = SF(vecC), *Mv = SF(vecD);
+  float *D = SF(efcD), *aref = SF(efcAref), *jar = SF(efcJar), *jv = SF(efcJv);
+  const float* J = SF(J);
+  const float* con = SF(con);
+  const uint32_t* pairs = CU(pair_pack);
+  const int base = 2 * dm.nlim, nrow = base + 4 * ncon;
+  if (lane < nv) Ma[lane] = matvec_row(M, ldm, nv, a, lane);
+  rows_mul(c, ncon, a, jar, aref);
+  int it = 0;
+  bool stalled = false;
+  for (;; it++) {
+    // gradient = M a - qfrc_smooth - J' f
+    float g = 0.f;
+    if (lane < nv) {
+      g = Ma[lane] - qfrc[lane];
+      for (int k = 0; k < ncon; k++) {
+        float mu = con[CON_STRIDE * k + CON_MU];
+        float f0 = jar[base + 4 * k] < 0 ? -D[base + 4 * k] * jar[base + 4 * k] : 0.f;
+        float f1 = jar[base + 4 * k + 1] < 0 ? -D[base + 4 * k + 1] * jar[base + 4 * k + 1] : 0.f;
+        float f2 = jar[base + 4 * k + 2] < 0 ? -D[base + 4 * k + 2] * jar[base + 4 * k + 2] : 0.f;
+        float f3_ = jar[base + 4 * k + 3] < 0 ? -D[base + 4 * k + 3] * jar[base + 4 * k + 3] : 0.f;
+        g -= J[(3 * k) * dm.ldj + lane] * (f0 + f1 + f2 + f3_) + J[(3 * k + 1) * dm.ldj + lane] * mu * (f0 - f1) +
+             J[(3 * k + 2) * dm.ldj + lane] * mu * (f2 - f3_);
+      }
+      grad[lane] = g;
+    }
+    MJB_SYNC();
+    for (int k = lane; k < dm.nlim; k += 32) {
+      float flo = jar[2 * k] < 0 ? -D[2 * k] * jar[2 * k] : 0.f, fhi = jar[2 * k + 1] < 0 ? -D[2 * k + 1] * jar[2 * k + 1] : 0.f;
+      grad[CI(lim_dof)[k]] -= flo - fhi;
+    }
+    MJB_SYNC();
+    g = lane < nv ? grad[lane] : 0.f;
+    float gn = wsum(g * g);
+    float fn = wsum(lane < nv ? qfrc[lane] * qfrc[lane] + Ma[lane] * Ma[lane] : 0.f);
+    if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) break;
+    // Hessian H = M + J' diag(D active) J (lower triangle)
+    for (int i = lane; i < nv * ldm; i += 32) H[i] = M[i];
+    MJB_SYNC();
+    for (int k = lane; k < dm.nlim; k += 32) {
+      int d = CI(lim_dof)[k];
+      H[d * ldm + d] += (jar[2 * k] < 0 ? D[2 * k] : 0.f) + (jar[2 * k + 1] < 0 ? D[2 * k + 1] : 0.f);
+    }
+    MJB_SYNC();
+    for (int k = 0; k < ncon; k++) {
+      uint32_t pk = pairs[((const int*)(con + CON_STRIDE * k))[CON_PAIR]];
+      int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
+      uint32_t mask = (b1 >= 0 ? CU(mb_dofmask)[2 * b1] : 0u) ^ (b2 >= 0 ? CU(mb_dofmask)[2 * b2] : 0u);
+      float mu = con[CON_STRIDE * k + CON_MU];
+      float w0 = jar[base + 4 * k] < 0 ? D[base + 4 * k] : 0.f, w1 = jar[base + 4 * k + 1] < 0 ? D[base + 4 * k + 1] : 0.f;
+      float w2 = jar[base + 4 * k + 2] < 0 ? D[base + 4 * k + 2] : 0.f, w3 = jar[base + 4 * k + 3] < 0 ? D[base + 4 * k + 3] : 0.f;
+      float cnn = w0 + w1 + w2 + w3;
+      if (cnn == 0.f) continue;  // warp-uniform
+      float cn1 = mu * (w0 - w1), c11 = mu * mu * (w0 + w1), cn2 = mu * (w2 - w3), c22 = mu * mu * (w2 + w3);
+      bool mine = lane < nv && ((mask >> lane) & 1u);
+      float jn = 0.f, j1 = 0.f, j2 = 0.f;
+      if (mine) { jn = J[(3 * k) * dm.ldj + lane]; j1 = J[(3 * k + 1) * dm.ldj + lane]; j2 = J[(3 * k + 2) * dm.ldj + lane]; }
+      // row i (lane) x column j (set bits of mask, j <= i)
+      float ri_n = cnn * jn + cn1 * j1 + cn2 * j2, ri_1 = cn1 * jn + c11 * j1, ri_2 = cn2 * jn + c22 * j2;
+      uint32_t mm = mask;
+      while (mm) {
+        int j = MJB_FFS(mm) - 1;
+        mm &= mm - 1;
+        if (mine && j <= lane)
+          H[lane * ldm + j] += ri_n * J[(3 * k) * dm.ldj + j] + ri_1 * J[(3 * k + 1) * dm.ldj + j] + ri_2 * J[(3 * k + 2) * dm.ldj + j];
+      }
+    }
+    MJB_SYNC();
+    float invd = cholesky(H, ldm, nv, lane);
+    float s = chol_solve(H, ldm, nv, lane, invd, lane < nv ? -g : 0.f);
+    if (lane < nv) sv[lane] = s;
+    MJB_SYNC();
+    float mv = 0.f;
+    if (lane < nv) { mv = matvec_row(M, ldm, nv, sv, lane); Mv[lane] = mv; }
+    rows_mul(c, ncon, sv, jv, nullptr);
+    float p1 = wsum(lane < nv ? s * (Ma[lane] - qfrc[lane]) : 0.f);
+    float p2 = wsum(lane < nv ? s * mv : 0.f);
+    // exact line search on the convex piecewise-quadratic phi(alpha): safeguarded Newton on phi'
+    float alpha = 0.f, lo = 0.f, hi = MJB_BIG, d1_0 = 0.f;
+    for (int ls = 0; ls <= dm.ls_iterations; ls++) {
+      float d1 = 0.f, d2 = 0.f;
+      for (int r = lane; r < nrow; r += 32) {
+        float x = jar[r] + alpha * jv[r];
+        if (x < 0.f) { d1 += D[r] * x * jv[r]; d2 += D[r] * jv[r] * jv[r]; }
+      }
+      d1 = wsum(d1) + p1 + alpha * p2;
+      d2 = wsum(d2) + p2;
+      if (ls == 0) d1_0 = d1;
+      else {
+        if (fabsf(d1) <= 1e-6f * fabsf(d1_0)) break;
+        if (d1 < 0.f) lo = alpha; else hi = alpha;
+      }
+      if (ls == dm.ls_iterations) break;
+      float nxt = alpha - d1 / fmaxf(d2, MJB_MINVAL);
+      if (!(nxt > lo && nxt < hi)) nxt = hi < MJB_BIG ? 0.5f * (lo + hi) : (alpha > 0.f ? 2.f * alpha : 1.f);
+      alpha = nxt;
+    }
+    float amax = wmax(lane < nv ? fabsf(a[lane]) : 0.f), smax = wmax(fabsf(alpha * s));
+    stalled = smax <= 1e-7f * (1.f + amax);
+    if (lane < nv) { a[lane] += alpha * s; Ma[lane] += alpha * mv; }
+    for (int r = lane; r < nrow; r += 32) jar[r] += alpha * jv[r];
+    MJB_SYNC();
+  }
+  return it;
+}
+
+// =================================================================================================
+// ray casting
+MJB_DEV int quad_roots(float a, float b, float cc, float* x) {
+  if (a < MJB_MINVAL) return 0;
+  float det = b * b - a * cc;
+  if (det < 0) return 0;
+  float sq = sqrtf(det);
+  x[0] = (-b - sq) / a; x[1] = (-b + sq) / a;
+  return 2;
+}
+MJB_DEV float ray_geom(f3 pos, const float* R, const float* size, f3 pnt, f3 vec, int type) {
+  if (type == MJB_GEOM_SPHERE) {
+    f3 d = pnt - pos;
+    float x[2];
+    if (!quad_roots(dot(vec, vec), dot(vec, d), dot(d, d) - size[0] * size[0], x)) return -1.f;
+    return x[0] >= 0 ? x[0] : (x[1] >= 0 ? x[1] : -1.f);
+  }
+  f3 lp = mulTv(R, pnt - pos), lv = mulTv(R, vec);
+  if (type == MJB_GEOM_PLANE) {
+    if (lv.z > -MJB_MINVAL) return -1.f;
+    float x = -lp.z / lv.z;
+    if (x < 0) return -1.f;
+    float p0 = lp.x + x * lv.x, p1 = lp.y + x * lv.y;
+    if ((size[0] <= 0 || fabsf(p0) <= size[0]) && (size[1] <= 0 || fabsf(p1) <= size[1])) return x;
+    return -1.f;
+  }
+  float best = -1.f;
+  if (type == MJB_GEOM_CAPSULE) {
+    float r = size[0], h = size[1], x[2];
+    if (quad_roots(lv.x * lv.x + lv.y * lv.y, lp.x * lv.x + lp.y * lv.y, lp.x * lp.x + lp.y * lp.y - r * r, x))
+      for (int i = 0; i < 2; i++)
+        if (fabsf(lp.z + x[i] * lv.z) <= h && x[i] >= 0 && (best < 0 || x[i] < best)) best = x[i];
+    for (int sg = -1; sg <= 1; sg += 2) {
+      f3 d = lp - mk3(0, 0, sg * h);
+      if (quad_roots(dot(lv, lv), dot(lv, d), dot(d, d) - r * r, x))
+        for (int i = 0; i < 2; i++)
+          if (sg * (lp.z + x[i] * lv.z) >= h && x[i] >= 0 && (best < 0 || x[i] < best)) best = x[i];
+    }
+    return best;
+  }
+  // box
+  for (int a = 0; a < 3; a++) {
+    float lva = comp(lv, a), lpa = comp(lp, a);
+    if (fabsf(lva) < MJB_MINVAL) continue;
+    int a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+    for (int sg = -1; sg <= 1; sg += 2) {
+      float t = (sg * size[a] - lpa) / lva;
+      if (t < 0) continue;
+      if (fabsf(comp(lp, a1) + t * comp(lv, a1)) <= size[a1] && fabsf(comp(lp, a2) + t * comp(lv, a2)) <= size[a2])
+        if (best < 0 || t < best) best = t;
+    }
+  }
+  return best;
+}
+
+MJB_DEV float cutoff(const Ctx& c, int i, float x) {
+  float cut = CF(sensor_cutoff)[i];
+  if (cut <= 0) return x;
+  int dt = CI(sensor_dtype)[i];
+  if (dt == 0) return fminf(cut, fmaxf(-cut, x));
+  if (dt == 1) return fminf(cut, x);
+  return x;
+}
+
+// position-stage sensors (rangefinder, frame axes)
+MJB_DEV void sensors_pos(const Ctx& c) {
+  const DevModel& dm = *c.dm;
+  float* sens = SF(sens);
+  for (int i = 0; i < dm.nsensor; i++) {
+    int type = CI(sensor_type)[i], t = CI(sensor_site)[i], adr = CI(sensor_adr)[i];
+    if (type == MJB_SENS_RANGEFINDER) {
+      f3 pnt = ld3(SF(spos) + 3 * t), vec = colv(SF(smat) + 9 * t, 2);
+      int bex = CI(site_mb)[t];
+      float best = MJB_BIG;
+      for (int g = c.lane; g < dm.ngeom; g += 32) {
+        int gb = CI(geom_mb)[g];
+        if ((gb >= 0 && gb == bex) || !CI(geom_ray)[g]) continue;
+        GeomW gw = geom_world(c, g);
+        float x = ray_geom(gw.pos, gw.mat, gw.size, pnt, vec, gw.type);
+        if (x >= 0 && x < best) best = x;
+      }
+      best = wmin(best);
+      if (c.lane == 0) sens[adr] = cutoff(c, i, best >= MJB_BIG ? -1.f : best);
+    } else if (type >= MJB_SENS_FRAMEXAXIS && type <= MJB_SENS_FRAMEZAXIS) {
+      if (c.lane < 3) sens[adr + c.lane] = cutoff(c, i, SF(smat)[9 * t + 3 * c.lane + (type - MJB_SENS_FRAMEXAXIS)]);
+    }
+  }
+  MJB_SYNC();
+}
+
+// acceleration-stage sensors (touch, accelerometer); needs the solved qacc and efcJar
+MJB_DEV void sensors_acc(const Ctx& c, int ncon) {
+  const DevModel& dm = *c.dm;
+  if (!dm.need_acc_sensors) return;
+  float* sens = SF(sens);
+  bool did_rne = false;
+  const uint32_t* pairs = CU(pair_pack);
+  const int base = 2 * dm.nlim;
+  for (int i = 0; i < dm.nsensor; i++) {
+    int type = CI(sensor_type)[i], t = CI(sensor_site)[i], adr = CI(sensor_adr)[i];
+    if (type == MJB_SENS_TOUCH) {
+      int body = CI(site_mb)[t];
+      float total = 0.f;
+      for (int k = c.lane; k < ncon; k += 32) {
+        const float* r = SF(con) + CON_STRIDE * k;
+        uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
+        int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
+        if (body < 0 || (b1 != body && b2 != body)) continue;
+        float fn = 0.f;
+        for (int e = 0; e < 4; e++) {
+          float x = SF(efcJar)[base + 4 * k + e];
+          if (x < 0) fn -= SF(efcD)[base + 4 * k + e] * x;
+        }
+        if (fn <= MJB_MINVAL) continue;
+        f3 ray = ld3(r + CON_FRAME);
+        if (b2 == body) ray = ray * -1.f;
+        if (ray_geom(ld3(SF(spos) + 3 * t), SF(smat) + 9 * t, CF(site_size) + 3 * t, ld3(r + CON_POS), ray, CI(site_type)[t]) >= 0)
+          total += fn;
+      }
+      total = wsum(total);
+      if (c.lane == 0) sens[adr] = cutoff(c, i, total);
+    } else if (type == MJB_SENS_ACCELEROMETER) {
+      if (!did_rne) { rne_pass(c, true); did_rne = true; }
+      int b = CI(site_mb)[t];
+      if (c.lane == 0) {
+        f3 acc = mk3(-dm.gravity[0], -dm.gravity[1], -dm.gravity[2]);
+        if (b >= 0) {
+          f3 w = ld3(SF(cvel) + 6 * b), v = ld3(SF(cvel) + 6 * b + 3), aw = ld3(SF(cacc) + 6 * b), av = ld3(SF(cacc) + 6 * b + 3);
+          f3 r = ld3(SF(spos) + 3 * t) - ld3(SF(xpos) + 3 * CI(mb_root)[b]);
+          acc = av + cross(aw, r) + cross(w, v + cross(w, r));
+        }
+        f3 loc = mulTv(SF(smat) + 9 * t, acc);
+        sens[adr] = cutoff(c, i, loc.x); sens[adr + 1] = cutoff(c, i, loc.y); sens[adr + 2] = cutoff(c, i, loc.z);
+      }
+    }
+  }
+  MJB_SYNC();
+}
+
+// =================================================================================================
+// one forward-dynamics evaluation: SF_qpos / qvel / ctrl -> SF_qacc.  Returns the contact count.
+MJB_DEV int forward(const Ctx& c, bool sensors, int* iters_out) {
+  fk(c);
+  crb_mass(c);
+  rne_pass(c, false);
+  int ncon = collide(c);
+  if (sensors) sensors_pos(c);
+  make_constraints(c, ncon);
+  int it = newton(c, ncon);
+  if (iters_out) *iters_out = it;
+  if (sensors) sensors_acc(c, ncon);
+  return ncon;
+}
+
+// qpos += h * qvel-like `v` (lane = joint)
+MJB_DEV void integrate_pos(const Ctx& c, float* qpos, const float* v, float h) {
+  const DevModel& dm = *c.dm;
+  for (int j = c.lane; j < dm.njnt; j += 32) {
+    int qa = CI(jnt_qposadr)[j], da = CI(jnt_dofadr)[j];
+    if (CI(jnt_type)[j] == MJB_JNT_FREE) {
+      for (int i = 0; i < 3; i++) qpos[qa + i] += h * v[da + i];
+      f3 w = ld3(v + da + 3);
+      float nw = sqrtf(dot(w, w)), ang = nw * h;
+      if (ang > 0.f) {
+        q4 q = qnorm(qmul(ldq(qpos + qa + 3), axisangle(w * (1.0f / nw), ang)));
+        qpos[qa + 3] = q.w; qpos[qa + 4] = q.x; qpos[qa + 5] = q.y; qpos[qa + 6] = q.z;
+      }
+    } else {
+      qpos[qa] += h * v[da];
+    }
+  }
+}
+
+// one mj_step (forward + integration).  `last` selects sensor evaluation (only the final substep's
+// sensors are observable).  SF_qacc keeps the solver's qacc (not the damping-corrected one): it is
+// the warm start of the next solve, as MuJoCo's qacc_warmstart.
+MJB_DEV int substep(const Ctx& c, bool last, int* iters_out) {
+  const DevModel& dm = *c.dm;
+  const int nv = dm.nv, lane = c.lane;
+  float *qpos = SF(qpos), *qvel = SF(qvel), *qacc = SF(qacc);
+  float h = dm.timestep;
+  int ncon = forward(c, last, iters_out);
+  if (dm.integrator == MJB_INT_EULER) {
+    float acc = lane < nv ? qacc[lane] : 0.f;
+    if (dm.has_damping) {
+      // (M + h D) a' = qfrc_smooth + qfrc_constraint  ( = M a - gradient at the solver's exit point)
+      float *M = SF(M), *H = SF(H);
+      for (int i = lane; i < nv * dm.ldm; i += 32) H[i] = M[i];
+      MJB_SYNC();
+      if (lane < nv) H[lane * dm.ldm + lane] += h * CF(dof_damping)[lane];
+      MJB_SYNC();
+      float rhs = lane < nv ? SF(vecA)[lane] - SF(vecB)[lane] : 0.f;
+      float invd = cholesky(H, dm.ldm, nv, lane);
+      acc = chol_solve(H, dm.ldm, nv, lane, invd, rhs);
+    }
+    if (lane < nv) qvel[lane] += h * acc;
+    MJB_SYNC();
+    integrate_pos(c, qpos, qvel, h);
+    MJB_SYNC();
+  } else {
+    // RK4 (classical tableau); stages 2..4 re-evaluate the forward dynamics without sensors
+    float* rk = SF(rk);
+    float *q0 = rk, *v0 = rk + dm.nq, *dq = rk + dm.nq + nv, *dv = rk + dm.nq + 2 * nv;
+    const float A[3] = {0.5f, 0.5f, 1.0f}, Bw[4] = {1.f / 6, 1.f / 3, 1.f / 3, 1.f / 6};
+    for (int i = lane; i < dm.nq; i += 32) q0[i] = qpos[i];
+    if (lane < nv) { v0[lane] = qvel[lane]; dq[lane] = Bw[0] * qvel[lane]; dv[lane] = Bw[0] * qacc[lane]; }
+    MJB_SYNC();
+    for (int st = 1; st < 4; st++) {
+      // stage state: q = q0 (+) h A x_{st-1}.v ; v = v0 + h A f_{st-1}
+      float vprev = lane < nv ? qvel[lane] : 0.f, aprev = lane < nv ? qacc[lane] : 0.f;
+      MJB_SYNC();
+      if (lane < nv) { SF(vecC)[lane] = A[st - 1] * vprev; }
+      for (int i = lane; i < dm.nq; i += 32) qpos[i] = q0[i];
+      MJB_SYNC();
+      integrate_pos(c, qpos, SF(vecC), h);
+      if (lane < nv) qvel[lane] = v0[lane] + h * A[st - 1] * aprev;
+      MJB_SYNC();
+      ncon = forward(c, false, nullptr);
+      if (lane < nv) { dq[lane] += Bw[st] * qvel[lane]; dv[lane] += Bw[st] * qacc[lane]; }
+      MJB_SYNC();
+    }
+    if (lane < nv) qvel[lane] = v0[lane] + h * dv[lane];
+    for (int i = lane; i < dm.nq; i += 32) qpos[i] = q0[i];
+    MJB_SYNC();
+    integrate_pos(c, qpos, dq, h);
+    MJB_SYNC();
+  }
+  return ncon;
+}
+
+}  // namespace mjb
