@@ -174,6 +174,8 @@ int64_t mjb_launch_count(const mjb_batch* b);
  * recorded around each launch when enabled with mjb_set_timing(b, 1) */
 int mjb_set_timing(mjb_batch* b, int32_t enable);
 int mjb_kernel_time_ms(mjb_batch* b, double* total_ms, int64_t* launches);
+/* launch geometry chosen at creation: CTAs, env-warps per CTA, dynamic shared memory per CTA */
+int mjb_batch_geometry(const mjb_batch* b, int32_t* grid, int32_t* warps_per_cta, int64_t* smem_bytes);
 /* counter-based draw used for target selection: exported so tests can reproduce the stream */
 uint32_t mjb_draw_u32(uint64_t seed, uint32_t env, uint32_t agent, uint32_t counter);
 

@@ -1,0 +1,111 @@
+"""Batch: `num_envs` lock-stepped environments on one GPU behind the C-ABI (include/mjb.h).
+
+Plays the role of `MjData` x num_envs (MuJoCo_Gym/mujoco_parent.py:127): all state lives in torch
+CUDA tensors owned here (row-major, env-major, rows 16 B aligned); the library only gets raw device
+pointers.  There is no CPU fallback: constructing a Batch without a CUDA device raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+class Batch:
+    def __init__(self, model: "L.Model", spec: "L.EnvSpec", num_envs: int, device=None, keepalive=()):
+        self._lib = L.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("mujoco_rl_environment_wrapper_b200: no CUDA device — the step path is CUDA-only "
+                               "(sm_100a); there is no CPU fallback")
+        self.model, self.spec, self.num_envs = model, spec, int(num_envs)
+        self._keep = keepalive
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        lay = L.Layout()
+        L.check(self._lib.mjb_batch_layout(model._h, ctypes.byref(spec), self.num_envs, ctypes.byref(lay)), "batch layout")
+        self.layout = lay
+        A, N, dev = spec.n_agents, self.num_envs, self.device
+        f32, i32, u8 = torch.float32, torch.int32, torch.uint8
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        self.buf = {
+            "qpos": z((N, lay.qpos_stride), f32), "qvel": z((N, lay.qvel_stride), f32),
+            "ctrl": z((N, lay.ctrl_stride), f32), "warmstart": z((N, lay.qvel_stride), f32),
+            "sensordata": z((N, lay.sensor_stride), f32), "probe": z((N, max(1, lay.probe_count), 4), f32),
+            "actions": z((N, max(1, A), lay.act_stride), f32), "obs": z((N, max(1, A), lay.obs_stride), f32),
+            "reward": z((N, max(1, A)), f32), "term": z((N, A + 1), u8), "trunc": z((N, A + 1), u8),
+            "timestep": z((N,), i32), "store_i": z((N, max(1, A), lay.store_i32), i32),
+            "store_f": z((N, max(1, A), lay.store_f32), f32), "ncon": z((N,), i32),
+            "contact_geom": z((N, lay.maxcon, 2), i32), "contact_dist": z((N, lay.maxcon), f32),
+        }
+        B = L.Buffers()
+        for k, v in self.buf.items():
+            setattr(B, k, v.data_ptr())
+        self._B = B
+        self.stream = torch.cuda.current_stream(dev)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            L.check(self._lib.mjb_batch_create(model._h, ctypes.byref(spec), self.num_envs, dev.index or 0,
+                                               ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(B), ctypes.byref(h)),
+                    "batch create")
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.mjb_batch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def __getattr__(self, k):
+        buf = self.__dict__.get("buf")
+        if buf is not None and k in buf:
+            return buf[k]
+        raise AttributeError(k)
+
+    # ---- device-side entry points (asynchronous on self.stream)
+    def reset(self, mask=None):
+        p = None
+        if mask is not None:
+            self._mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            p = ctypes.c_void_p(self._mask.data_ptr())
+        L.check(self._lib.mjb_reset(self._h, p), "reset")
+
+    def step(self):
+        L.check(self._lib.mjb_step(self._h), "step")
+
+    def physics(self, skip_frames=1):
+        L.check(self._lib.mjb_physics(self._h, skip_frames), "physics")
+
+    def forward(self):
+        L.check(self._lib.mjb_forward(self._h), "forward")
+
+    def sync(self):
+        L.check(self._lib.mjb_sync(self._h), "sync")
+
+    # ---- host-buffer step: numpy in / numpy out, copies inside
+    def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, term: np.ndarray, trunc: np.ndarray):
+        L.check(self._lib.mjb_step_host(self._h, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data,
+                                        term.ctypes.data, trunc.ctypes.data), "step_host")
+
+    def host_arrays(self):
+        lay, A, N = self.layout, self.spec.n_agents, self.num_envs
+        return (np.zeros((N, A, lay.act_stride), np.float32), np.zeros((N, A, lay.obs_stride), np.float32),
+                np.zeros((N, A), np.float32), np.zeros((N, A + 1), np.uint8), np.zeros((N, A + 1), np.uint8))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.mjb_launch_count(self._h))
+
+    def set_timing(self, enable=True):
+        L.check(self._lib.mjb_set_timing(self._h, 1 if enable else 0))
+
+    def kernel_time_ms(self):
+        t, n = ctypes.c_double(), ctypes.c_int64()
+        L.check(self._lib.mjb_kernel_time_ms(self._h, ctypes.byref(t), ctypes.byref(n)))
+        return t.value, n.value
+
+    def geometry(self):
+        g, w, s = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+        self._lib.mjb_batch_geometry(self._h, ctypes.byref(g), ctypes.byref(w), ctypes.byref(s))
+        return {"grid": g.value, "warps_per_cta": w.value, "smem_bytes": s.value}

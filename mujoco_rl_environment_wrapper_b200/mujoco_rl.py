@@ -1,0 +1,460 @@
+"""Drop-in `MuJoCoRL` over the batched CUDA step path.
+
+Mirrors the reference's public surface (MuJoCo_Gym/mujoco_rl.py:18-430, mujoco_parent.py:19-478):
+`MuJoCoRL(config_dict)`, `reset()`, `step(action_dict)`, `action_space(agent)`,
+`observation_space(agent)`, `filter_by_tag`, `get_data`, `distance`, `collision`,
+`get_observations`, `get_sensor_data`, attributes `agents`, `possible_agents`, `data_store`,
+`timestep`, `max_steps`, `skip_frames`, `action_routing`, `agents_action_index`,
+`agents_observation_index`.
+
+New optional config keys: `num_envs` (default 1), `device`, `seed`, `probes` (extra body / geom
+names whose positions are exported every step).  With `num_envs == 1` results are squeezed to the
+reference's shapes (numpy arrays, Python scalars); otherwise every per-agent value is a CUDA tensor
+with a leading `num_envs` dimension.  There is no CPU path: construction raises without a GPU.
+"""
+import ctypes
+import json
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .batch import Batch
+from .spaces import Box
+from .tables import Tables
+
+
+class AgentStore(dict):
+    """`env.data_store[agent]`: plain dict for user plugins; the fused plugins' keys are views of the
+    device store columns (`utterance`, `current_target`, `inventory`, `distance`, `xpos_before`)."""
+
+    def __init__(self, env, a):
+        super().__init__()
+        self._env, self._a = env, a
+
+    def _col(self, key):
+        b = self._env._batch
+        if key in ("utterance", "inventory"):
+            return b.store_i[:, self._a, L.STORE_I[key]]
+        if key == "current_target":
+            return b.store_i[:, self._a, L.STORE_I["current_target"]] - 1
+        if key in L.STORE_F:
+            return b.store_f[:, self._a, L.STORE_F[key]]
+        return None
+
+    def __missing__(self, key):
+        col = self._col(key)
+        if col is None:
+            raise KeyError(key)
+        return col if self._env.num_envs > 1 else col[0].item()
+
+
+class MuJoCoRL:
+    metadata = {"name": "mujoco_rl_b200"}
+
+    def __init__(self, config_dict: dict):
+        self.agents = config_dict.get("agents", [])
+        self.possible_agents = self.agents
+        self.xml_paths = config_dict.get("xmlPath")
+        self.info_jsons = config_dict.get("infoJson", None)
+        self.render_mode = config_dict.get("renderMode", False)
+        self.export_path = config_dict.get("exportPath")
+        self.free_joint = config_dict.get("freeJoint", False)
+        self.skip_frames = config_dict.get("skipFrames", 1)
+        self.max_steps = config_dict.get("maxSteps", 1024)
+        self.reward_functions = list(config_dict.get("rewardFunctions", []))
+        self.done_functions = list(config_dict.get("doneFunctions", []))
+        dynamics_classes = list(config_dict.get("environmentDynamics", []))
+        self.agent_cameras = config_dict.get("agentCameras", False)  # accepted, cameras are not observations
+        self.num_envs = int(config_dict.get("num_envs", 1))
+        self.seed = int(config_dict.get("seed", 1234))
+        self._extra_probes = list(config_dict.get("probes", []))
+        dev = config_dict.get("device", None)
+        if not torch.cuda.is_available():
+            raise RuntimeError("MuJoCoRL (B200): no CUDA device available; this implementation has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if dev is None else torch.device(dev)
+        if not self.agents:
+            raise Exception("config_dict['agents'] must name at least one agent body")
+        if len(self.agents) > L.MAX_AGENTS:
+            raise Exception(f"at most {L.MAX_AGENTS} agents are supported")
+
+        self.timestep = 0
+        self.action_routing = {"physical": [], "dynamic": {}}
+        # xml (str or list -> random.choice, mujoco_parent.py:88-91)
+        self.xml_path = self.xml_paths if isinstance(self.xml_paths, str) else random.choice(self.xml_paths)
+        with open(self.xml_path, "r") as fh:
+            self._xml_text = fh.read()
+        self.model = L.Model(self._xml_text)
+        self.__instantiate_json()
+        self._tables = Tables(self._xml_text, self.model, self.agents, self.free_joint)
+        self.agents_action_index = self._tables.agents_action_index
+        self.agents_observation_index = self._tables.agents_observation_index
+
+        self.data_store = {agent: AgentStore(self, a) for a, agent in enumerate(self.agents)}
+        self.environment_dynamics = [dyn(self) for dyn in dynamics_classes]
+        self.__build_spaces()
+        self.__build_batch()
+        self.__check_dynamics(self.environment_dynamics)
+        self.__check_reward_functions(self.reward_functions)
+        self.__check_done_functions(self.done_functions)
+        self._wipe_store()
+
+    # ------------------------------------------------------------------------------------------
+    def __instantiate_json(self):
+        """mujoco_rl.py:93-112"""
+        if isinstance(self.info_jsons, list):
+            if len(self.info_jsons) != len(self.xml_paths):
+                raise Exception("Length mismatch between info_json list and xml_paths list")
+            tail = os.path.split(self.xml_path)[1]
+            json_file = tail.split(".")[0] + ".json"
+            json_file = [cur for cur in self.info_jsons if json_file in cur][0]
+            with open(json_file) as fh:
+                self.info_json = json.load(fh)
+            self.info_name_list = list(self.info_json["environment"]["objects"].keys())
+        elif isinstance(self.info_jsons, str):
+            with open(self.info_jsons) as fh:
+                self.info_json = json.load(fh)
+            self.info_name_list = list(self.info_json["environment"]["objects"].keys())
+        elif isinstance(self.info_jsons, dict):  # convenience: already-parsed json
+            self.info_json = self.info_jsons
+            self.info_name_list = list(self.info_json["environment"]["objects"].keys())
+        else:
+            self.info_json = None
+            self.info_name_list = []
+
+    def __build_spaces(self):
+        """mujoco_rl.py:171-213"""
+        self._observation_space, self._action_space = {}, {}
+        self._n_mj_obs = {}
+        for agent in self.agents:
+            osp = {k: list(v) for k, v in self._tables.obs_space[agent].items()}
+            self._n_mj_obs[agent] = len(osp["low"])
+            asp = {k: list(v) for k, v in self._tables.act_space[agent].items()}
+            self.action_routing["physical"] = [0, len(asp["low"])]
+            for dyn in self.environment_dynamics:
+                n0 = len(asp["low"])
+                self.action_routing["dynamic"][dyn.__class__.__name__] = [n0, n0 + len(dyn.action_space["low"])]
+                asp["low"] += list(dyn.action_space["low"])
+                asp["high"] += list(dyn.action_space["high"])
+                osp["low"] += list(dyn.observation_space["low"])
+                osp["high"] += list(dyn.observation_space["high"])
+            self._observation_space[agent] = Box(low=np.array(osp["low"], dtype=np.float32), high=np.array(osp["high"], dtype=np.float32))
+            self._action_space[agent] = Box(low=np.array(asp["low"], dtype=np.float32), high=np.array(asp["high"], dtype=np.float32))
+        n_phys = {len(self._tables.act_space[a]["low"]) for a in self.agents}
+        if len(n_phys) != 1:
+            raise Exception("all agents must have the same number of physical actions (mujoco_rl.py:182)")
+
+    def _targets(self):
+        if self.info_json is None:
+            return []
+        try:
+            return self.__filter_names("target")
+        except KeyError:
+            return []
+
+    def __filter_names(self, tag):
+        """names in filter_by_tag order, duplicates kept (mujoco_rl.py:355-378)"""
+        names = []
+        objs = self.info_json["environment"]["objects"]
+        for obj in objs:
+            if "tags" in objs[obj].keys() and objs[obj]["tags"] is not None and tag in objs[obj]["tags"]:
+                names.append(obj)
+        for area in self.info_json["areas"]:
+            aobjs = self.info_json["areas"][area]["objects"]
+            for obj in aobjs:
+                if "tags" in aobjs[obj].keys() and aobjs[obj]["tags"] is not None and tag in aobjs[obj]["tags"]:
+                    names.append(obj)
+        return names
+
+    def _resolve(self, name):
+        """name -> (objtype, id) with the reference's body-then-geom fallback (mujoco_parent.py:403-425)"""
+        bid = self.model.name2id(L.OBJ_BODY, name)
+        if bid >= 0:
+            return L.OBJ_BODY, bid
+        gid = self.model.name2id(L.OBJ_GEOM, name)
+        if gid >= 0:
+            return L.OBJ_GEOM, gid
+        raise KeyError(f"Invalid name '{name}': neither a body nor a geom")
+
+    def __build_batch(self):
+        A = len(self.agents)
+        spec = L.EnvSpec()
+        spec.n_agents, spec.free_joint = A, int(bool(self.free_joint))
+        spec.skip_frames, spec.max_steps = int(self.skip_frames), int(self.max_steps)
+        n_phys = len(self._tables.act_space[self.agents[0]]["low"])
+        spec.n_phys_act = n_phys
+        act_index, obs_index, adr = [], [], [0]
+        for a, agent in enumerate(self.agents):
+            act_index += self.agents_action_index[agent]
+            oi = self.agents_observation_index[agent]
+            obs_index += [(0 << 24) | i for i in oi["sensors"]] + [(1 << 24) | i for i in oi["qpos"]] + [(2 << 24) | i for i in oi["qvel"]]
+            adr.append(len(obs_index))
+            spec.agent_body[a] = self._tables.agent_body[agent]
+        for a in range(A + 1):
+            spec.obs_adr[a] = adr[a]
+        # plugins: fused kinds go to the kernel, the rest run as batched torch code after it
+        self._fused_dyn, self._host_dyn, self._host_rew, self._host_done = [], [], [], []
+        nd = nr = ndn = 0
+        act_pos = n_phys
+        fused_obs = 0
+        for dyn in self.environment_dynamics:
+            kind = getattr(dyn, "mjb_kind", None)
+            lo = act_pos
+            act_pos += len(dyn.action_space["low"])
+            if kind and kind[0] == "dynamic" and not self._host_dyn:
+                p = spec.dynamics[nd]
+                p.kind, p.act_lo, p.act_hi, p.n_obs = kind[1], lo, act_pos, len(dyn.observation_space["low"])
+                p.param[0] = float(getattr(dyn, "threshold", 0.0))
+                nd += 1
+                fused_obs += p.n_obs
+                self._fused_dyn.append(dyn)
+            else:
+                self._host_dyn.append((dyn, lo, act_pos))
+        for fn in self.reward_functions:
+            kind = getattr(fn, "mjb_kind", None)
+            if kind and kind[0] == "reward" and not self._host_rew:
+                p = spec.rewards[nr]
+                p.kind = kind[1]
+                p.param[0] = float(getattr(fn, "scale", 1.0))
+                nr += 1
+            else:
+                self._host_rew.append(fn)
+        for fn in self.done_functions:
+            kind = getattr(fn, "mjb_kind", None)
+            if kind and kind[0] == "done" and not self._host_done:
+                p = spec.dones[ndn]
+                p.kind = kind[1]
+                p.param[0] = float(getattr(fn, "threshold", 1.0))
+                ndn += 1
+            else:
+                self._host_done.append(fn)
+        spec.n_dynamics, spec.n_rewards, spec.n_dones = nd, nr, ndn
+        spec.act_dim = act_pos
+        self._act_dim = act_pos
+        for a, agent in enumerate(self.agents):
+            spec.obs_dim[a] = self._n_mj_obs[agent] + fused_obs
+        self._fused_obs = fused_obs
+        # targets (filter_by_tag("target")) and extra probes
+        self._target_names = self._targets()
+        if len(self._target_names) > L.MAX_TARGETS:
+            raise Exception(f"at most {L.MAX_TARGETS} tagged targets are supported")
+        self._probe_names = list(self.agents)
+        spec.n_targets = len(self._target_names)
+        for t, name in enumerate(self._target_names):
+            ot, oid = self._resolve(name)
+            spec.target_objtype[t], spec.target_objid[t] = ot, oid
+            self._probe_names.append(name)
+        spec.seed = self.seed
+        self._ai = (ctypes.c_int32 * max(1, len(act_index)))(*act_index)
+        self._oi = (ctypes.c_int32 * max(1, len(obs_index)))(*obs_index)
+        spec.act_index = ctypes.cast(self._ai, ctypes.POINTER(ctypes.c_int32))
+        spec.obs_index = ctypes.cast(self._oi, ctypes.POINTER(ctypes.c_int32))
+        self._spec = spec
+        with torch.cuda.device(self.device):
+            self._batch = Batch(self.model, spec, self.num_envs, device=self.device, keepalive=(self._ai, self._oi))
+        self._sample_gen = torch.Generator(device=self.device)
+        self._sample_gen.manual_seed(self.seed)
+        self._act_low = torch.tensor(np.asarray(self._action_space[self.agents[0]].low), device=self.device)
+        self._act_high = torch.tensor(np.asarray(self._action_space[self.agents[0]].high), device=self.device)
+
+    # ---- validators (mujoco_rl.py:114-169): run each plugin once for agents[0]
+    def __check_dynamics(self, dynamics):
+        for dyn in dynamics:
+            actions = dyn.action_space["low"]
+            reward, observations, done, info = dyn.dynamic(self.agents[0], torch.tensor(actions, dtype=torch.float32, device=self.device).reshape(1, -1).expand(self.num_envs, -1))
+            obs = torch.as_tensor(observations, dtype=torch.float32).reshape(-1, len(dyn.observation_space["low"])) if len(dyn.observation_space["low"]) else torch.zeros(1, 0)
+            lo = torch.tensor(dyn.observation_space["low"], dtype=torch.float32, device=obs.device)
+            hi = torch.tensor(dyn.observation_space["high"], dtype=torch.float32, device=obs.device)
+            if obs.shape[-1] != len(dyn.observation_space["low"]):
+                raise Exception(f"Observation, the second return variable of dynamic function, must match length"
+                                f" of lower bound of observation space of {dyn}")
+            if obs.numel() and not bool((obs >= lo).all()):
+                raise Exception(f"Observation, the second return variable of dynamic function, exceeds the lower bound"
+                                f" on at least one axis of the observation space of {dyn}")
+            if obs.numel() and not bool((obs <= hi).all()):
+                raise Exception(f"Observation, the second return variable of dynamic function, exceeds the upper bound"
+                                f" on at least one axis of the observation space of {dyn}")
+            if not (isinstance(reward, (int, float)) or torch.is_tensor(reward)):
+                raise Exception(f"Reward, the first return variable of dynamic function of {dyn}, must be a float")
+
+    def __check_done_functions(self, done_functions):
+        for fn in done_functions:
+            done = fn(self, self.agents[0])
+            if not (isinstance(done, int) or torch.is_tensor(done)):
+                raise Exception(f"Done, the first return variable of {fn}, must be a boolean")
+
+    def __check_reward_functions(self, reward_functions):
+        for fn in reward_functions:
+            reward = fn(self, self.agents[0])
+            if not (isinstance(reward, (int, float)) or torch.is_tensor(reward)):
+                raise Exception(f"Reward, the second return variable of {fn}, must be a float")
+
+    def _wipe_store(self):
+        b = self._batch
+        keep = b.store_i[:, :, L.STORE_I["draws"]].clone()
+        b.store_i.zero_()
+        b.store_i[:, :, L.STORE_I["draws"]] = keep
+        b.store_f.zero_()
+        for st in self.data_store.values():
+            st.clear()
+
+    # ------------------------------------------------------------------------------------------
+    def action_space(self, agent):
+        return self._action_space[agent]
+
+    def observation_space(self, agent):
+        return self._observation_space[agent]
+
+    def sample_actions(self):
+        """Uniform actions in [low, high) for every env and agent (device tensor [N, A, act_dim])."""
+        u = torch.rand((self.num_envs, len(self.agents), self._act_dim), generator=self._sample_gen, device=self.device)
+        return self._act_low + u * (self._act_high - self._act_low)
+
+    def _load_actions(self, action):
+        b = self._batch
+        if torch.is_tensor(action):  # packed [N, A, act_dim]
+            b.actions[:, :, :self._act_dim] = action.to(self.device, torch.float32).reshape(self.num_envs, len(self.agents), -1)
+            return
+        for a, agent in enumerate(self.agents):
+            v = action[agent]
+            t = v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v, dtype=np.float32))
+            b.actions[:, a, :self._act_dim] = t.to(self.device, torch.float32).reshape(-1, self._act_dim) if t.numel() else 0
+
+    def _out(self, t):
+        if self.num_envs > 1:
+            return t
+        return t[0].cpu().numpy().astype(np.float64) if t.dim() > 1 else t[0].item()
+
+    def _collect_obs(self, extra):
+        b = self._batch
+        out = {}
+        for a, agent in enumerate(self.agents):
+            o = b.obs[:, a, :self._spec.obs_dim[a]]
+            if extra and extra.get(agent):
+                o = torch.cat([o] + extra[agent], dim=1)
+            out[agent] = self._out(o)
+        return out
+
+    def step(self, action):
+        """mujoco_rl.py:243-289 for all envs at once (one fused kernel launch)."""
+        b = self._batch
+        self._load_actions(action)
+        b.step()
+        N = self.num_envs
+        rewards = {agent: b.reward[:, a] for a, agent in enumerate(self.agents)}
+        terms = {agent: b.term[:, a].bool() for a, agent in enumerate(self.agents)}
+        infos = {agent: {dyn.__class__.__name__: {} for dyn in self._fused_dyn} for agent in self.agents}
+        extra = {agent: [] for agent in self.agents}
+        for dyn, lo, hi in self._host_dyn:  # user dynamics as batched torch code, agent-inner order
+            for a, agent in enumerate(self.agents):
+                r, o, d, info = dyn.dynamic(agent, b.actions[:, a, lo:hi])
+                extra[agent].append(torch.as_tensor(o, dtype=torch.float32, device=self.device).reshape(N, -1))
+                rewards[agent] = rewards[agent] + r
+                terms[agent] = terms[agent] | torch.as_tensor(d, device=self.device).bool()
+                infos[agent][dyn.__class__.__name__] = info
+        for fn in self._host_rew:
+            rewards = {agent: rewards[agent] + fn(self, agent) for agent in self.agents}
+        truncs = {agent: b.trunc[:, a].bool() for a, agent in enumerate(self.agents)}
+        truncs["__all__"] = b.trunc[:, len(self.agents)].bool()
+        if self.done_functions:
+            for fn in self._host_done:
+                terms = {agent: terms[agent] | torch.as_tensor(fn(self, agent), device=self.device).bool() for agent in self.agents}
+            allt = terms[self.agents[0]].clone()
+            for agent in self.agents[1:]:
+                allt = allt | terms[agent]
+            terms["__all__"] = allt
+        self.timestep += 1
+        obs = self._collect_obs(extra)
+        if N == 1:
+            rewards = {k: (v[0].item() if torch.is_tensor(v) else v) for k, v in rewards.items()}
+            terms = {k: bool(v[0].item()) for k, v in terms.items()}
+            truncs = {k: bool(v[0].item()) for k, v in truncs.items()}
+        return obs, rewards, terms, truncs, infos
+
+    def reset(self, *, seed=None, options=None, mask=None):
+        """mujoco_rl.py:291-331.  `mask` (bool[N]) resets a subset of envs (new; the reference has one env)."""
+        b = self._batch
+        b.actions[:, :, :self._act_dim] = self.sample_actions()  # the reference applies dynamics once with a sampled action
+        b.reset(mask)
+        for st in self.data_store.values():
+            st.clear()
+        infos = {agent: {dyn.__class__.__name__: {} for dyn in self._fused_dyn} for agent in self.agents}
+        extra = {agent: [] for agent in self.agents}
+        for dyn, lo, hi in self._host_dyn:
+            for a, agent in enumerate(self.agents):
+                r, o, d, info = dyn.dynamic(agent, b.actions[:, a, lo:hi])
+                extra[agent].append(torch.as_tensor(o, dtype=torch.float32, device=self.device).reshape(self.num_envs, -1))
+                infos[agent][dyn.__class__.__name__] = info
+        for st in self.data_store.values():
+            st.clear()  # everything the dynamics wrote is discarded (mujoco_rl.py:326-328)
+        if mask is None:
+            self.timestep = 0
+        return self._collect_obs(extra), infos
+
+    # ---- queries (mujoco_parent.py:366-478, mujoco_rl.py:355-395)
+    def get_sensor_data(self, agent=None):
+        sd = self._batch.sensordata[:, :self.model.nsensordata]
+        if agent is not None:
+            sd = sd[:, self.agents_observation_index[agent]["sensors"]]
+        return self._out(sd)
+
+    def get_observations(self, agent):
+        b = self._batch
+        oi = self.agents_observation_index[agent]
+        o = torch.cat([b.sensordata[:, oi["sensors"]], b.qpos[:, oi["qpos"]], b.qvel[:, oi["qvel"]]], dim=1)
+        return self._out(o)
+
+    def _position(self, name_or_xyz):
+        if isinstance(name_or_xyz, str):
+            if name_or_xyz not in self._probe_names:
+                raise Exception(f"'{name_or_xyz}' is not an exported position: add it to config_dict['probes'] "
+                                f"(exported: {self._probe_names})")
+            return self._batch.probe[:, self._probe_names.index(name_or_xyz), :3]
+        return torch.as_tensor(name_or_xyz, dtype=torch.float32, device=self.device).reshape(-1, 3)
+
+    def distance(self, object_1, object_2):
+        d = (self._position(object_1) - self._position(object_2)).norm(dim=1)
+        return d if self.num_envs > 1 else d[0].item()
+
+    def collision(self, geom_1, geom_2):
+        def gid(g):
+            if isinstance(g, str):
+                i = self.model.name2id(L.OBJ_GEOM, g)
+                if i < 0:
+                    raise Exception(f"Collision object {g} not found in data")
+                return i
+            return int(g)
+        g1, g2 = gid(geom_1), gid(geom_2)
+        b = self._batch
+        cg = b.contact_geom
+        valid = torch.arange(cg.shape[1], device=self.device)[None, :] < b.ncon[:, None]
+        hit = ((cg[:, :, 0] == g1) & (cg[:, :, 1] == g2)) | ((cg[:, :, 0] == g2) & (cg[:, :, 1] == g1))
+        r = (hit & valid).any(dim=1)
+        return r if self.num_envs > 1 else bool(r[0].item())
+
+    def get_data(self, name):
+        ot, oid = self._resolve(name)
+        f = self.model.fields
+        pos = self._position(name) if name in self._probe_names else None
+        if pos is not None and self.num_envs == 1:
+            pos = pos[0].cpu().numpy().astype(np.float64)
+        if ot == L.OBJ_BODY:
+            data = {"position": pos, "mass": float(f["body_mass"][oid]), "id": oid, "name": name, "type": "body"}
+        else:
+            data = {"position": pos, "id": oid, "name": name, "type": "geom",
+                    "color": f["geom_rgba"][4 * oid:4 * oid + 4].copy(), "shape": int(f["geom_type"][oid])}
+        if name in self.info_name_list:
+            for key, val in self.info_json["environment"]["objects"][name].items():
+                if key not in ["position", "orientation", "mass"]:
+                    data[key] = val
+        return data
+
+    def filter_by_tag(self, tag):
+        return [self.get_data(n) for n in self.__filter_names(tag)]
+
+    # ---- raw device views for policy code
+    @property
+    def batch(self):
+        return self._batch

@@ -1,0 +1,108 @@
+"""The device step code (csrc/step_kernel.cuh + env_kernel.cuh), compiled for the host SIMT emulator,
+against the fp64 oracle from identical states.  Runs without a GPU; the same comparisons run through
+the C-ABI on the B200 in test_gpu_parity.py.  Tolerance: fp32 state after one step within
+rtol = 1e-4 of the fp64 result (|x_gpu - x_ref| <= 1e-4 * max(1, |x_ref|)), contact-pair sets exact."""
+import numpy as np
+import pytest
+
+import emu_harness as E
+from common import load_scene, make_spec, oracle_states
+from mujoco_rl_environment_wrapper_b200 import _lib as L
+from oracle import host_loop as H
+
+RTOL = 1e-4
+
+
+def rel_err(x, ref):
+    return float((np.abs(x - ref) / np.maximum(1.0, np.abs(ref))).max()) if len(ref) else 0.0
+
+
+@pytest.mark.parametrize("scene,n,stride,settle", [("2A", 24, 25, 150), ("1A", 10, 20, 40), ("S3", 12, 20, 100), ("3S", 8, 30, 150)])
+def test_one_step_parity(scene, n, stride, settle):
+    model, tables, agents, fj = load_scene(scene)
+    spec, keep = make_spec(model, tables, agents, fj)
+    states = oracle_states(model, tables, agents, fj, n, stride=stride, settle=settle)
+    eb = E.EmuBatch(model.blob, spec, len(states), keep)
+    nq, nv, nu, ns = model.nq, model.nv, model.nu, model.nsensordata
+    n_phys = spec.n_phys_act
+    for e, (pre, post) in enumerate(states):
+        eb.qpos[e, :nq], eb.qvel[e, :nv], eb.warmstart[e, :nv] = pre[0], pre[1], pre[2]
+        if nu:
+            eb.ctrl[e, :nu] = pre[3]
+        eb.actions[e, :, :n_phys] = pre[4]
+    eb.run(E.MODE_PHYSICS, 1)
+    seen_contacts = 0
+    for e, (pre, post) in enumerate(states):
+        assert rel_err(eb.qpos[e, :nq], post["qpos"]) < RTOL
+        assert rel_err(eb.qvel[e, :nv], post["qvel"]) < RTOL
+        if ns:
+            assert rel_err(eb.sensordata[e, :ns], post["sensordata"][:ns]) < RTOL
+        nc = eb.ncon[e]
+        assert sorted((int(a), int(b)) for a, b in eb.contact_geom[e, :nc]) == post["pairs"]
+        seen_contacts += nc
+    assert seen_contacts > 0, "the sample must exercise contacts"
+
+
+def test_lane_order_independence():
+    """Running the lanes in reverse order must not change a single bit (missing-barrier detector)."""
+    model, tables, agents, fj = load_scene("2A")
+    spec, keep = make_spec(model, tables, agents, fj)
+    states = oracle_states(model, tables, agents, fj, 4, stride=60, settle=200)
+    outs = []
+    for rev in (False, True):
+        eb = E.EmuBatch(model.blob, spec, len(states), keep)
+        for e, (pre, post) in enumerate(states):
+            eb.qpos[e, :model.nq], eb.qvel[e, :model.nv], eb.warmstart[e, :model.nv] = pre[0], pre[1], pre[2]
+            eb.actions[e, :, :8] = pre[4]
+        eb.run(E.MODE_PHYSICS, 2, reverse=rev)
+        outs.append((eb.qpos.copy(), eb.qvel.copy(), eb.sensordata.copy()))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
+def _resolver(model):
+    def resolve(name):
+        b = model.name2id(L.OBJ_BODY, name)
+        return (1, b) if b >= 0 else (5, model.name2id(L.OBJ_GEOM, name))
+    return resolve
+
+
+def test_full_step_with_plugins_against_host_loop():
+    """C2: Language + tag-distance reward + done, state re-synchronised every step so that the epilogue
+    (ordering, draws, flags) is compared exactly."""
+    model, tables, agents, fj = load_scene("2A")
+    lib = L.load()
+    targets = ["choice_1", "choice_2"]
+    tspec = [(L.OBJ_BODY, model.name2id(L.OBJ_BODY, t)) for t in targets]
+    seed, max_steps = 99, 6
+    spec, keep = make_spec(model, tables, agents, fj, max_steps=max_steps, dynamics=[(L.DYN_LANGUAGE, 1, 1, 0.0)],
+                           rewards=[(L.REW_TAG_DISTANCE, 10.0)], dones=[(L.DONE_DISTANCE_LE, 1.0)], targets=tspec, seed=seed)
+    env = H.OracleEnv(model, tables, agents, max_steps=max_steps, dynamics=[H.Language],
+                      reward_functions=[H.tag_distance_reward], done_functions=[H.distance_done], targets=targets,
+                      draw=lambda a, k: lib.mjb_draw_u32(seed, 0, a, k), resolve=_resolver(model))
+    eb = E.EmuBatch(model.blob, spec, 1, keep)
+    rng = np.random.default_rng(11)
+    act0 = {a: np.concatenate([rng.uniform(-1, 1, 8), rng.uniform(0, 3, 1)]) for a in agents}
+    obs, _ = env.reset(act0)
+    eb.actions[0, :, :9] = np.stack([act0[a] for a in agents])
+    eb.run(E.MODE_RESET)
+    for i, a in enumerate(agents):
+        assert rel_err(eb.obs[0, i, :60], obs[a]) < RTOL
+        assert eb.obs[0, i, 59] == obs[a][59]
+    assert not eb.store_i[0, :, :5].any() and eb.timestep[0] == 0
+    nq, nv = model.nq, model.nv
+    for t in range(9):
+        act = {a: np.concatenate([rng.uniform(-1, 1, 8), rng.uniform(0, 3, 1)]) for a in agents}
+        eb.qpos[0, :nq], eb.qvel[0, :nv], eb.warmstart[0, :nv] = env.sim.qpos, env.sim.qvel, env.sim.qacc_warmstart
+        eb.actions[0, :, :9] = np.stack([act[a] for a in agents])
+        o, r, term, trunc, _ = env.step(act)
+        eb.run(E.MODE_STEP, 1)
+        for i, a in enumerate(agents):
+            assert rel_err(eb.obs[0, i, :59], o[a][:59]) < RTOL
+            assert eb.obs[0, i, 59] == o[a][59]                       # Language: integer, exact
+            assert abs(eb.reward[0, i] - r[a]) < 1e-3                 # 10 * delta of fp32 distances
+            assert bool(eb.term[0, i]) == term[a] and bool(eb.trunc[0, i]) == trunc[a]
+        assert bool(eb.term[0, 2]) == term["__all__"] and bool(eb.trunc[0, 2]) == trunc["__all__"]
+        assert eb.timestep[0] == env.timestep
+        tgt = [targets.index(env.data_store[a]["current_target"]) + 1 for a in agents]
+        assert list(eb.store_i[0, :, L.STORE_I["current_target"]]) == tgt
