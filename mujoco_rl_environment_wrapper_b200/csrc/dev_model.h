@@ -50,6 +50,8 @@ namespace mjb {
   X(dof_mb)         /* int [nv]                                                                  */ \
   X(dof_parent)     /* int [nv]                                                                  */ \
   X(dof_kind)       /* int [nv]        0 hinge/slide axis in body, 1 free translation, 2 free rotation */ \
+  X(dof_t0)         /* int [32]        first dof of the lane's kinematic tree (lane = dof)        */ \
+  X(dof_t1)         /* int [32]        one past the last dof of that tree (0 for lanes >= nv)     */ \
   X(dof_armature)   /* f32 [nv]                                                                  */ \
   X(dof_damping)    /* f32 [nv]                                                                  */ \
   X(geom_type)      /* int [ngeom]                                                               */ \
@@ -120,7 +122,7 @@ struct DevPlugin {
 struct DevModel {
   // sizes
   int nq, nv, nu, nmb, njnt, nlim, ngeom, ngdyn, nsite, nsensor, nsensordata, npair, nclass, nlevel, nprobe;
-  int maxcon, maxcand, maxefc, ldm, ldj;
+  int maxcon, maxcand, maxefc, ldm, ldj, maxtree;
   int integrator, has_damping, need_acc_sensors;
   float timestep, gravity[3];
   int solver_iterations, ls_iterations;

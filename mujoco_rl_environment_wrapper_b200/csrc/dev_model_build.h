@@ -185,6 +185,22 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
     if (m.jnt_type[j] == MJB_JNT_FREE) w.i(d - m.jnt_dofadr[j] < 3 ? DOF_FREE_TRANS : DOF_FREE_ROT);
     else w.i(DOF_AXIS);
   }
+  {
+    // kinematic-tree dof ranges (trees own contiguous dof ranges); used to factor block by block
+    std::vector<int> t0(32, 0), t1(32, 0);
+    int maxtree = 0;
+    for (int d = 0; d < m.nv; d++) {
+      int lo = d, hi = d;
+      int tree = m.body_treeid[m.dof_bodyid[d]];
+      while (lo > 0 && m.body_treeid[m.dof_bodyid[lo - 1]] == tree) lo--;
+      while (hi + 1 < m.nv && m.body_treeid[m.dof_bodyid[hi + 1]] == tree) hi++;
+      t0[d] = lo; t1[d] = hi + 1;
+      maxtree = std::max(maxtree, hi + 1 - lo);
+    }
+    dm.maxtree = maxtree;
+    w.begin(IF_dof_t0); for (int v : t0) w.i(v);
+    w.begin(IF_dof_t1); for (int v : t1) w.i(v);
+  }
   w.begin(IF_dof_armature); for (int d = 0; d < m.nv; d++) w.f(m.dof_armature[d]);
   w.begin(IF_dof_damping);
   for (int d = 0; d < m.nv; d++) { w.f(m.dof_damping[d]); if (m.dof_damping[d] > 0) dm.has_damping = 1; }
@@ -344,7 +360,7 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   dm.image_words = (int)W.size();
 
   // ---- limits on per-env scratch
-  int dflt_con = ngdyn >= 16 ? 16 : 8;
+  int dflt_con = ngdyn >= 16 ? 12 : 8;
   dm.maxcon = std::max(1, env_int("MJB_MAXCON", dflt_con));
   dm.maxcand = std::max(32, std::min(m.npair, env_int("MJB_MAXCAND", 160)));
   dm.maxefc = 2 * dm.nlim + 4 * dm.maxcon;
@@ -357,7 +373,8 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   sizes[SF_cdof] = 6 * nv; sizes[SF_cinert] = 10 * nmb; sizes[SF_crb] = 10 * nmb; sizes[SF_cvel] = 6 * nmb; sizes[SF_cacc] = 6 * nmb;
   sizes[SF_gpos] = 3 * std::max(1, ngdyn); sizes[SF_gmat] = 9 * std::max(1, ngdyn);
   sizes[SF_spos] = 3 * std::max(1, m.nsite); sizes[SF_smat] = 9 * std::max(1, m.nsite);
-  sizes[SF_M] = nv * dm.ldm; sizes[SF_H] = nv * dm.ldm;
+  const int tri = nv * (nv + 1) / 2;  // packed lower triangle
+  sizes[SF_M] = tri; sizes[SF_H] = tri;
   sizes[SF_cand] = dm.maxcand;
   sizes[SF_con] = CON_STRIDE * dm.maxcon;
   sizes[SF_J] = 3 * dm.maxcon * dm.ldj;
@@ -365,8 +382,18 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   sizes[SF_vecA] = sizes[SF_vecB] = sizes[SF_vecC] = sizes[SF_vecD] = nv;
   sizes[SF_rk] = m.integrator == MJB_INT_RK4 ? (m.nq + 3 * nv) : 1;
   sizes[SF_sens] = std::max(1, m.nsensordata);
+  // lifetime aliasing: the Hessian lives where cinert + crb were (dead once the bias forces are known),
+  // the broad-phase candidate list where cvel + cacc are (dead between the bias pass and the sensors)
+  const bool alias_H = tri <= r4(sizes[SF_cinert]) + r4(sizes[SF_crb]);
+  if (dm.maxcand > r4(sizes[SF_cvel]) + r4(sizes[SF_cacc])) dm.maxcand = std::max(32, r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]) - 4);
+  const bool alias_cand = dm.maxcand <= r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]);
+  sizes[SF_cand] = dm.maxcand;
   int off = 0;
-  for (int i = 0; i < SF_COUNT; i++) { dm.soff[i] = off; off += r4(sizes[i]); }
+  for (int i = 0; i < SF_COUNT; i++) {
+    if (i == SF_H && alias_H) { dm.soff[i] = dm.soff[SF_cinert]; continue; }
+    if (i == SF_cand && alias_cand) { dm.soff[i] = dm.soff[SF_cvel]; continue; }
+    dm.soff[i] = off; off += r4(sizes[i]);
+  }
   dm.env_words = off;
 
   // ---- HBM row strides (16-byte aligned rows)

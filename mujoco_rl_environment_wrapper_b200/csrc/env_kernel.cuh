@@ -175,8 +175,10 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
     MJB_SYNC();
   }
   int ncon = -1;
-  if (mode == MODE_FORWARD || mode == MODE_RESET) ncon = forward(c, true, nullptr);
-  else for (int f = 0; f < skip_frames; f++) ncon = substep(c, f == skip_frames - 1, nullptr);
+  // mj_forward (reset / forward modes) is one pass of the same loop body without integration
+  const bool integrate = !(mode == MODE_FORWARD || mode == MODE_RESET);
+  const int passes = integrate ? skip_frames : 1;
+  for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, nullptr);
   if (ncon >= 0) {
     // exported positions come from the last forward pass, i.e. BEFORE the last integration
     for (int p = lane; p < dm.nprobe; p += 32) {

@@ -90,6 +90,11 @@ struct Ctx {
 #define SF(f) (c.s + c.dm->soff[SF_##f])
 #define SI(f) ((int*)(c.s + c.dm->soff[SF_##f]))
 
+// packed lower triangle: element (i, j), j <= i.  Lane i reading (i, k) is bank-conflict free for
+// i < 32 (triangular numbers are distinct mod 32).
+MJB_DEV int tri(int i, int j) { return ((i * (i + 1)) >> 1) + j; }
+MJB_DEV int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
+
 // spatial helpers: motion [w; v], force [n; f], inertia {m, h(3), I(6: xx yy zz xy xz yz)} about o
 MJB_DEV void inertia_mul(const float* I, f3 w, f3 v, f3& n, f3& f) {
   f3 h = mk3(I[1], I[2], I[3]);
@@ -209,7 +214,7 @@ MJB_DEV void crb_mass(const Ctx& c) {
   const int* level_adr = CI(level_adr);
   float *cinert = SF(cinert), *crb = SF(crb), *M = SF(M), *cdof = SF(cdof);
   for (int i = c.lane; i < 10 * dm.nmb; i += 32) crb[i] = cinert[i];
-  for (int i = c.lane; i < dm.nv * dm.ldm; i += 32) M[i] = 0.f;
+  for (int i = c.lane; i < (dm.nv * (dm.nv + 1)) / 2; i += 32) M[i] = 0.f;
   MJB_SYNC();
   for (int l = dm.nlevel - 2; l >= 0; l--) {
     for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
@@ -236,8 +241,7 @@ MJB_DEV void crb_mass(const Ctx& c) {
     for (int j = i; j >= 0; j = CI(dof_parent)[j]) {
       float v = dot(ld3(cdof + 6 * j), n) + dot(ld3(cdof + 6 * j + 3), f);
       if (j == i) v += CF(dof_armature)[i];
-      M[i * dm.ldm + j] = v;
-      M[j * dm.ldm + i] = v;
+      M[tri(i, j)] = v;  // j is an ancestor dof: j <= i
     }
   }
   MJB_SYNC();
@@ -463,7 +467,10 @@ MJB_DEV int collide(const Ctx& c) {
       GeomW a = geom_world(c, g1), b = geom_world(c, g2);
       float rb2 = CF(geom_rbound)[g2];
       if (a.type == MJB_GEOM_PLANE) keep = dot(b.pos - a.pos, colv(a.mat, 2)) <= rb2 + margin;
-      else {
+      else if (b.type == MJB_GEOM_BOX) {
+        // bounding sphere of geom1 against the oriented box itself: long thin boxes have useless spheres
+        keep = point_box_dist(mulTv(b.mat, a.pos - b.pos), b.size) <= CF(geom_rbound)[g1] + margin;
+      } else {
         float rr = CF(geom_rbound)[g1] + rb2 + margin;
         f3 d = b.pos - a.pos;
         keep = dot(d, d) <= rr * rr;
@@ -578,6 +585,11 @@ MJB_DEV int collide(const Ctx& c) {
 
 // =================================================================================================
 // constraints
+// general-power sigmoid (rare: the default power is 2) kept out of line to keep the hot code small
+MJB_DEV_NOINLINE float impedance_pow(float x, float mid, float power) {
+  if (x <= mid) return powf(x, power) / powf(mid, power - 1.f);
+  return 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+}
 MJB_DEV float impedance(const float* solimp, float pos, float margin) {
   float dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
   if (dmin == dmax || width <= MJB_MINVAL) return 0.5f * (dmin + dmax);
@@ -587,8 +599,7 @@ MJB_DEV float impedance(const float* solimp, float pos, float margin) {
   float y;
   if (power == 1.f) y = x;
   else if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
-  else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
-  else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  else y = impedance_pow(x, mid, power);
   return dmin + y * (dmax - dmin);
 }
 
@@ -671,42 +682,67 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
 }
 
 // =================================================================================================
-// dense helpers (nv <= 32: lane = row)
-// out[row] = sum_j A[row][j] x[j]
-MJB_DEV float matvec_row(const float* A, int ld, int n, const float* x, int row) {
-  float s = 0.f;
-  for (int j = 0; j < n; j++) s += A[row * ld + j] * x[j];
-  return s;
+// dense helpers (nv <= 32: lane = row / dof).  M is block diagonal over kinematic trees and so is the
+// Hessian unless a contact couples two trees, so everything works per block [t0, t1) of the lane and the
+// blocks of different trees proceed in parallel on their own lanes.
+// out = sum_j A(row, j) x[j] over the row's block, A symmetric packed
+MJB_DEV float matvec_row(const float* A, const float* x, int row, int t0, int t1) {
+  float s0 = 0.f, s1 = 0.f;
+  int j = t0;
+  for (; j + 1 <= row && j + 1 < t1; j += 2) { s0 += A[tri(row, j)] * x[j]; s1 += A[tri(row, j + 1)] * x[j + 1]; }
+  for (; j <= row && j < t1; j++) s0 += A[tri(row, j)] * x[j];
+  for (; j < t1; j++) s1 += A[tri(j, row)] * x[j];
+  return s0 + s1;
 }
-// in-place Cholesky of the lower triangle; lane i owns row i.  Returns 1/L_ii of the lane's row.
-MJB_DEV float cholesky(float* A, int ld, int n, int lane) {
+// in-place Cholesky of the packed lower triangle, block by block; lane i owns row i.  `nb` = the largest
+// block size (warp-uniform).  Returns 1 / L_ii of the lane's row.
+MJB_DEV float cholesky(float* A, int lane, int t0, int t1, int nb) {
   float invd = 1.f;
-  for (int j = 0; j < n; j++) {
-    float s = 0.f;
-    if (lane >= j && lane < n) {
-      s = A[lane * ld + j];
-      for (int k = 0; k < j; k++) s -= A[lane * ld + k] * A[j * ld + k];
+  const bool own = lane < t1;  // lanes >= nv have t0 = t1 = 0
+  for (int jj = 0; jj < nb; jj++) {
+    const int j = t0 + jj;
+    const bool col = own && j < t1;
+    float s0 = 0.f, s1 = 0.f;
+    if (col && lane >= j) {
+      s0 = A[tri(lane, j)];
+      const float* ri = A + tri(lane, 0);
+      const float* rj = A + tri(j, 0);
+      int k = t0;
+      for (; k + 1 < j; k += 2) { s0 -= ri[k] * rj[k]; s1 -= ri[k + 1] * rj[k + 1]; }
+      if (k < j) s0 -= ri[k] * rj[k];
     }
-    float sj = MJB_SHFL(s, j);
+    float s = s0 + s1;
+    float sj = MJB_SHFL(s, col ? j : lane);
     float inv = MJB_RSQRT(fmaxf(sj, 1e-20f));
-    if (lane == j) { invd = inv; A[lane * ld + j] = sj * inv; }
-    else if (lane > j && lane < n) A[lane * ld + j] = s * inv;
+    if (col) {
+      if (lane == j) { invd = inv; A[tri(lane, j)] = sj * inv; }
+      else if (lane > j) A[tri(lane, j)] = s * inv;
+    }
     MJB_SYNC();
   }
   return invd;
 }
-// solve L L' x = b with lane-resident b/x
-MJB_DEV float chol_solve(const float* A, int ld, int n, int lane, float invd, float b) {
+// solve L L' x = b with lane-resident b / x
+MJB_DEV float chol_solve(const float* A, int lane, int t0, int t1, int nb, float invd, float b) {
   float x = b;
-  for (int k = 0; k < n; k++) {
-    float yk = MJB_SHFL(x * invd, k);
-    if (lane == k) x = yk;
-    else if (lane > k && lane < n) x -= A[lane * ld + k] * yk;
+  const bool own = lane < t1;
+  for (int kk = 0; kk < nb; kk++) {
+    const int k = t0 + kk;
+    const bool col = own && k < t1;
+    float yk = MJB_SHFL(x * invd, col ? k : lane);
+    if (col) {
+      if (lane == k) x = yk;
+      else if (lane > k) x -= A[tri(lane, k)] * yk;
+    }
   }
-  for (int k = n - 1; k >= 0; k--) {
-    float xk = MJB_SHFL(x * invd, k);
-    if (lane == k) x = xk;
-    else if (lane < k) x -= A[k * ld + lane] * xk;
+  for (int kk = nb - 1; kk >= 0; kk--) {
+    const int k = t0 + kk;
+    const bool col = own && k < t1;
+    float xk = MJB_SHFL(x * invd, col ? k : lane);
+    if (col) {
+      if (lane == k) x = xk;
+      else if (lane < k && lane >= t0) x -= A[tri(k, lane)] * xk;
+    }
   }
   return x;
 }
@@ -723,9 +759,12 @@ MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const 
   const float* con = SF(con);
   int base = 2 * dm.nlim;
   for (int r = c.lane; r < 3 * ncon; r += 32) {
-    float s = 0.f;
-    for (int d = 0; d < dm.nv; d++) s += J[r * dm.ldj + d] * x[d];
-    out[base + 4 * (r / 3) + (r % 3)] = s;
+    float s0 = 0.f, s1 = 0.f;
+    const float* jr = J + r * dm.ldj;
+    int d = 0;
+    for (; d + 1 < dm.nv; d += 2) { s0 += jr[d] * x[d]; s1 += jr[d + 1] * x[d + 1]; }
+    if (d < dm.nv) s0 += jr[d] * x[d];
+    out[base + 4 * (r / 3) + (r % 3)] = s0 + s1;
   }
   MJB_SYNC();
   for (int k = c.lane; k < ncon; k += 32) {
@@ -743,14 +782,15 @@ MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const 
 // On exit SF_vecA = M qacc, SF_vecB = gradient, SF_efcJar = J qacc - aref.  Returns iterations used.
 MJB_DEV int newton(const Ctx& c, int ncon) {
   const DevModel& dm = *c.dm;
-  const int nv = dm.nv, lane = c.lane, ldm = dm.ldm;
+  const int nv = dm.nv, lane = c.lane;
+  const int t0 = CI(dof_t0)[lane], t1 = CI(dof_t1)[lane];
   float *M = SF(M), *H = SF(H), *a = SF(qacc), *qfrc = SF(qfrc), *Ma = SF(vecA), *grad = SF(vecB), *sv = SF(vecC), *Mv = SF(vecD);
   float *D = SF(efcD), *aref = SF(efcAref), *jar = SF(efcJar), *jv = SF(efcJv);
   const float* J = SF(J);
   const float* con = SF(con);
   const uint32_t* pairs = CU(pair_pack);
   const int base = 2 * dm.nlim, nrow = base + 4 * ncon;
-  if (lane < nv) Ma[lane] = matvec_row(M, ldm, nv, a, lane);
+  if (lane < nv) Ma[lane] = matvec_row(M, a, lane, t0, t1);
   rows_mul(c, ncon, a, jar, aref);
   int it = 0;
   bool stalled = false;
@@ -780,14 +820,15 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     float gn = wsum(g * g);
     float fn = wsum(lane < nv ? qfrc[lane] * qfrc[lane] + Ma[lane] * Ma[lane] : 0.f);
     if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) break;
-    // Hessian H = M + J' diag(D active) J (lower triangle)
-    for (int i = lane; i < nv * ldm; i += 32) H[i] = M[i];
+    // Hessian H = M + J' diag(D active) J (packed lower triangle)
+    for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) H[i] = M[i];
     MJB_SYNC();
     for (int k = lane; k < dm.nlim; k += 32) {
       int d = CI(lim_dof)[k];
-      H[d * ldm + d] += (jar[2 * k] < 0 ? D[2 * k] : 0.f) + (jar[2 * k + 1] < 0 ? D[2 * k + 1] : 0.f);
+      H[tri(d, d)] += (jar[2 * k] < 0 ? D[2 * k] : 0.f) + (jar[2 * k + 1] < 0 ? D[2 * k + 1] : 0.f);
     }
     MJB_SYNC();
+    bool coupled = false;  // does an active contact couple two kinematic trees?
     for (int k = 0; k < ncon; k++) {
       uint32_t pk = pairs[((const int*)(con + CON_STRIDE * k))[CON_PAIR]];
       int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
@@ -797,6 +838,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       float w2 = jar[base + 4 * k + 2] < 0 ? D[base + 4 * k + 2] : 0.f, w3 = jar[base + 4 * k + 3] < 0 ? D[base + 4 * k + 3] : 0.f;
       float cnn = w0 + w1 + w2 + w3;
       if (cnn == 0.f) continue;  // warp-uniform
+      if (b1 >= 0 && b2 >= 0 && CI(mb_root)[b1] != CI(mb_root)[b2]) coupled = true;
       float cn1 = mu * (w0 - w1), c11 = mu * mu * (w0 + w1), cn2 = mu * (w2 - w3), c22 = mu * mu * (w2 + w3);
       bool mine = lane < nv && ((mask >> lane) & 1u);
       float jn = 0.f, j1 = 0.f, j2 = 0.f;
@@ -808,16 +850,18 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
         int j = MJB_FFS(mm) - 1;
         mm &= mm - 1;
         if (mine && j <= lane)
-          H[lane * ldm + j] += ri_n * J[(3 * k) * dm.ldj + j] + ri_1 * J[(3 * k + 1) * dm.ldj + j] + ri_2 * J[(3 * k + 2) * dm.ldj + j];
+          H[tri(lane, j)] += ri_n * J[(3 * k) * dm.ldj + j] + ri_1 * J[(3 * k + 1) * dm.ldj + j] + ri_2 * J[(3 * k + 2) * dm.ldj + j];
       }
     }
     MJB_SYNC();
-    float invd = cholesky(H, ldm, nv, lane);
-    float s = chol_solve(H, ldm, nv, lane, invd, lane < nv ? -g : 0.f);
+    // factor per tree block unless a contact couples trees (then one block over all dofs)
+    const int h0 = coupled ? 0 : t0, h1 = coupled ? (lane < nv ? nv : 0) : t1, hb = coupled ? nv : dm.maxtree;
+    float invd = cholesky(H, lane, h0, h1, hb);
+    float s = chol_solve(H, lane, h0, h1, hb, invd, lane < nv ? -g : 0.f);
     if (lane < nv) sv[lane] = s;
     MJB_SYNC();
     float mv = 0.f;
-    if (lane < nv) { mv = matvec_row(M, ldm, nv, sv, lane); Mv[lane] = mv; }
+    if (lane < nv) { mv = matvec_row(M, sv, lane, t0, t1); Mv[lane] = mv; }
     rows_mul(c, ncon, sv, jv, nullptr);
     float p1 = wsum(lane < nv ? s * (Ma[lane] - qfrc[lane]) : 0.f);
     float p2 = wsum(lane < nv ? s * mv : 0.f);
@@ -1023,60 +1067,71 @@ MJB_DEV void integrate_pos(const Ctx& c, float* qpos, const float* v, float h) {
   }
 }
 
-// one mj_step (forward + integration).  `last` selects sensor evaluation (only the final substep's
-// sensors are observable).  SF_qacc keeps the solver's qacc (not the damping-corrected one): it is
-// the warm start of the next solve, as MuJoCo's qacc_warmstart.
-MJB_DEV int substep(const Ctx& c, bool last, int* iters_out) {
+// One mj_forward (`integrate` = false) or one mj_step (forward + integration).  `sensors` selects sensor
+// evaluation (only the final substep's sensors are observable).  The forward pass has ONE call site: Euler
+// is a single stage, RK4 four stages of the same loop (stages 2..4 without sensors).  SF_qacc keeps the
+// solver's qacc (not the damping-corrected one): it is the warm start of the next solve, as MuJoCo's
+// qacc_warmstart.
+MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) {
   const DevModel& dm = *c.dm;
   const int nv = dm.nv, lane = c.lane;
   float *qpos = SF(qpos), *qvel = SF(qvel), *qacc = SF(qacc);
-  float h = dm.timestep;
-  int ncon = forward(c, last, iters_out);
-  if (dm.integrator == MJB_INT_EULER) {
-    float acc = lane < nv ? qacc[lane] : 0.f;
-    if (dm.has_damping) {
-      // (M + h D) a' = qfrc_smooth + qfrc_constraint  ( = M a - gradient at the solver's exit point)
-      float *M = SF(M), *H = SF(H);
-      for (int i = lane; i < nv * dm.ldm; i += 32) H[i] = M[i];
-      MJB_SYNC();
-      if (lane < nv) H[lane * dm.ldm + lane] += h * CF(dof_damping)[lane];
-      MJB_SYNC();
-      float rhs = lane < nv ? SF(vecA)[lane] - SF(vecB)[lane] : 0.f;
-      float invd = cholesky(H, dm.ldm, nv, lane);
-      acc = chol_solve(H, dm.ldm, nv, lane, invd, rhs);
-    }
-    if (lane < nv) qvel[lane] += h * acc;
-    MJB_SYNC();
-    integrate_pos(c, qpos, qvel, h);
-    MJB_SYNC();
-  } else {
-    // RK4 (classical tableau); stages 2..4 re-evaluate the forward dynamics without sensors
-    float* rk = SF(rk);
-    float *q0 = rk, *v0 = rk + dm.nq, *dq = rk + dm.nq + nv, *dv = rk + dm.nq + 2 * nv;
-    const float A[3] = {0.5f, 0.5f, 1.0f}, Bw[4] = {1.f / 6, 1.f / 3, 1.f / 3, 1.f / 6};
-    for (int i = lane; i < dm.nq; i += 32) q0[i] = qpos[i];
-    if (lane < nv) { v0[lane] = qvel[lane]; dq[lane] = Bw[0] * qvel[lane]; dv[lane] = Bw[0] * qacc[lane]; }
-    MJB_SYNC();
-    for (int st = 1; st < 4; st++) {
-      // stage state: q = q0 (+) h A x_{st-1}.v ; v = v0 + h A f_{st-1}
+  const float h = dm.timestep;
+  const bool rk4 = integrate && dm.integrator == MJB_INT_RK4;
+  const int nstage = rk4 ? 4 : 1;
+  float* rk = SF(rk);
+  float *q0 = rk, *v0 = rk + dm.nq, *dq = rk + dm.nq + nv, *dv = rk + dm.nq + 2 * nv;
+  int ncon = 0;
+  for (int st = 0; st < nstage; st++) {
+    if (st > 0) {
+      // stage state: q = q0 (+) h A x_{st-1}.v ; v = v0 + h A f_{st-1}   (A = 1/2, 1/2, 1)
+      const float A = st == 3 ? 1.0f : 0.5f;
       float vprev = lane < nv ? qvel[lane] : 0.f, aprev = lane < nv ? qacc[lane] : 0.f;
       MJB_SYNC();
-      if (lane < nv) { SF(vecC)[lane] = A[st - 1] * vprev; }
+      if (lane < nv) SF(vecC)[lane] = A * vprev;
       for (int i = lane; i < dm.nq; i += 32) qpos[i] = q0[i];
       MJB_SYNC();
       integrate_pos(c, qpos, SF(vecC), h);
-      if (lane < nv) qvel[lane] = v0[lane] + h * A[st - 1] * aprev;
-      MJB_SYNC();
-      ncon = forward(c, false, nullptr);
-      if (lane < nv) { dq[lane] += Bw[st] * qvel[lane]; dv[lane] += Bw[st] * qacc[lane]; }
+      if (lane < nv) qvel[lane] = v0[lane] + h * A * aprev;
       MJB_SYNC();
     }
+    ncon = forward(c, sensors && st == 0, st == 0 ? iters_out : nullptr);
+    if (rk4) {
+      const float Bw = (st == 0 || st == 3) ? (1.f / 6) : (1.f / 3);
+      if (st == 0) {
+        for (int i = lane; i < dm.nq; i += 32) q0[i] = qpos[i];
+        if (lane < nv) { v0[lane] = qvel[lane]; dq[lane] = 0.f; dv[lane] = 0.f; }
+      }
+      if (lane < nv) { dq[lane] += Bw * qvel[lane]; dv[lane] += Bw * qacc[lane]; }
+      MJB_SYNC();
+    }
+  }
+  if (!integrate) return ncon;
+  if (rk4) {
     if (lane < nv) qvel[lane] = v0[lane] + h * dv[lane];
     for (int i = lane; i < dm.nq; i += 32) qpos[i] = q0[i];
     MJB_SYNC();
     integrate_pos(c, qpos, dq, h);
     MJB_SYNC();
+    return ncon;
   }
+  float acc = lane < nv ? qacc[lane] : 0.f;
+  if (dm.has_damping) {
+    // (M + h D) a' = qfrc_smooth + qfrc_constraint  ( = M a - gradient at the solver's exit point)
+    float *M = SF(M), *H = SF(H);
+    const int t0 = CI(dof_t0)[lane], t1 = CI(dof_t1)[lane];
+    for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) H[i] = M[i];
+    MJB_SYNC();
+    if (lane < nv) H[tri(lane, lane)] += h * CF(dof_damping)[lane];
+    MJB_SYNC();
+    float rhs = lane < nv ? SF(vecA)[lane] - SF(vecB)[lane] : 0.f;
+    float invd = cholesky(H, lane, t0, t1, dm.maxtree);
+    acc = chol_solve(H, lane, t0, t1, dm.maxtree, invd, rhs);
+  }
+  if (lane < nv) qvel[lane] += h * acc;
+  MJB_SYNC();
+  integrate_pos(c, qpos, qvel, h);
+  MJB_SYNC();
   return ncon;
 }
 

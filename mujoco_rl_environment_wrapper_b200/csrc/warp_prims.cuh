@@ -10,6 +10,7 @@
 #if defined(MJB_HOST_EMU)
 #include "../../tests/emu/simt_emu.h"
 #define MJB_DEV inline
+#define MJB_DEV_NOINLINE inline
 #define MJB_LANE() (simt::lane())
 #define MJB_SYNC() simt::barrier()
 #define MJB_SHFL(v, src) simt::shfl((v), (src))
@@ -20,6 +21,7 @@
 #define MJB_RSQRT(x) (1.0f / sqrtf(x))
 #else
 #define MJB_DEV __device__ __forceinline__
+#define MJB_DEV_NOINLINE __device__ __noinline__
 #define MJB_LANE() ((int)(threadIdx.x & 31))
 #define MJB_SYNC() __syncwarp()
 #define MJB_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))

@@ -417,6 +417,9 @@ void collision(Sim& s) {
     if (m.geom_type[g1] == MJB_GEOM_PLANE) {
       V3 n = col(gmat(s, g1), 2);
       if (dot(gpos(s, g2) - gpos(s, g1), n) > m.geom_rbound[g2] + margin) continue;
+    } else if (m.geom_type[g2] == MJB_GEOM_BOX) {
+      // conservative cull against the oriented box itself (bounding spheres of long boxes are useless)
+      if (point_box_dist(mulTv(gmat(s, g2), gpos(s, g1) - gpos(s, g2)), &m.geom_size[3 * g2]) > m.geom_rbound[g1] + margin) continue;
     } else {
       if (norm(gpos(s, g2) - gpos(s, g1)) > m.geom_rbound[g1] + m.geom_rbound[g2] + margin) continue;
     }
