@@ -388,11 +388,27 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   if (dm.maxcand > r4(sizes[SF_cvel]) + r4(sizes[SF_cacc])) dm.maxcand = std::max(32, r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]) - 4);
   const bool alias_cand = dm.maxcand <= r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]);
   sizes[SF_cand] = dm.maxcand;
+  // the per-row constraint vectors and the nv-sized solver temporaries live where xquat + xmat + xipos
+  // were: those are dead once the kinematics pass has produced geom frames, inertias and probes
+  const int solver_fields[8] = {SF_efcD, SF_efcAref, SF_efcJar, SF_efcJv, SF_vecC, SF_vecD, SF_vecA, SF_vecB};
+  const int dead_words = r4(sizes[SF_xquat]) + r4(sizes[SF_xmat]) + r4(sizes[SF_xipos]);
+  bool aliased[SF_COUNT] = {false};
+  {
+    int used = 0;  // greedy: as many of the solver fields as fit into the dead region
+    for (int f : solver_fields)
+      if (used + r4(sizes[f]) <= dead_words) { aliased[f] = true; used += r4(sizes[f]); }
+  }
   int off = 0;
   for (int i = 0; i < SF_COUNT; i++) {
     if (i == SF_H && alias_H) { dm.soff[i] = dm.soff[SF_cinert]; continue; }
     if (i == SF_cand && alias_cand) { dm.soff[i] = dm.soff[SF_cvel]; continue; }
+    if (aliased[i]) continue;  // placed below
     dm.soff[i] = off; off += r4(sizes[i]);
+  }
+  {
+    int o = dm.soff[SF_xquat];
+    for (int f : solver_fields)
+      if (aliased[f]) { dm.soff[f] = o; o += r4(sizes[f]); }
   }
   dm.env_words = off;
 

@@ -140,8 +140,8 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
 }
 
 // whole per-env pipeline.  Every lane of the warp calls this with the same arguments.
-MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int skip_frames, const uint8_t* reset_mask,
-                     float* probe /* shared, 4 * nprobe floats */) {
+MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int skip_frames, const uint8_t* reset_mask) {
+  float* probe = c.probe;
   const DevModel& dm = *c.dm;
   const int lane = c.lane;
   if (mode == MODE_RESET && reset_mask && !reset_mask[env]) return;
@@ -180,12 +180,6 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
   const int passes = integrate ? skip_frames : 1;
   for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, nullptr);
   if (ncon >= 0) {
-    // exported positions come from the last forward pass, i.e. BEFORE the last integration
-    for (int p = lane; p < dm.nprobe; p += 32) {
-      int kind = CI(probe_kind)[p], id = CI(probe_id)[p];
-      f3 v = kind == PROBE_BODY ? ld3(SF(xipos) + 3 * id) : (kind == PROBE_GEOM ? ld3(SF(gpos) + 3 * id) : ld3(CF(probe_const) + 3 * p));
-      probe[4 * p] = v.x; probe[4 * p + 1] = v.y; probe[4 * p + 2] = v.z; probe[4 * p + 3] = 0.f;
-    }
     if (B.ncon && lane == 0) B.ncon[env] = ncon;
     if (B.contact_geom) {
       const uint32_t* pairs = CU(pair_pack);

@@ -62,9 +62,9 @@ __global__ void k_env(const __grid_constant__ DevModel dm, const uint32_t* __res
   mbar_wait(bar, 0);
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
-  Ctx c{&dm, img, scratch, lane};
+  Ctx c{&dm, img, scratch, lane, probe};
   for (int env = blockIdx.x * warps + warp; env < num_envs; env += gridDim.x * warps) {
-    run_env(c, B, env, mode, skip_frames, mask, probe);
+    run_env(c, B, env, mode, skip_frames, mask);
     __syncwarp();
   }
 }

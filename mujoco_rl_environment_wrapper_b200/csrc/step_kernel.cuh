@@ -83,6 +83,7 @@ struct Ctx {
   const uint32_t* img;  // constant image (shared memory)
   float* s;             // this env's scratch (shared memory)
   int lane;
+  float* probe;         // exported positions of this env (shared memory, 4 floats per probe)
 };
 #define CI(f) ((const int*)(c.img + c.dm->off[IF_##f]))
 #define CU(f) ((const uint32_t*)(c.img + c.dm->off[IF_##f]))
@@ -1037,6 +1038,17 @@ MJB_DEV void sensors_acc(const Ctx& c, int ncon) {
 // one forward-dynamics evaluation: SF_qpos / qvel / ctrl -> SF_qacc.  Returns the contact count.
 MJB_DEV int forward(const Ctx& c, bool sensors, int* iters_out) {
   fk(c);
+  if (sensors) {
+    // exported positions belong to THIS forward pass, i.e. to the state before the integration that
+    // follows; taken now because xipos is recycled by the solver scratch below
+    const DevModel& dm = *c.dm;
+    for (int p = c.lane; p < dm.nprobe; p += 32) {
+      int kind = CI(probe_kind)[p], id = CI(probe_id)[p];
+      f3 v = kind == PROBE_BODY ? ld3(SF(xipos) + 3 * id) : (kind == PROBE_GEOM ? ld3(SF(gpos) + 3 * id) : ld3(CF(probe_const) + 3 * p));
+      c.probe[4 * p] = v.x; c.probe[4 * p + 1] = v.y; c.probe[4 * p + 2] = v.z; c.probe[4 * p + 3] = 0.f;
+    }
+    MJB_SYNC();
+  }
   crb_mass(c);
   rne_pass(c, false);
   int ncon = collide(c);
