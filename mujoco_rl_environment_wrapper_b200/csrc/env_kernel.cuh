@@ -39,13 +39,19 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
   bool done[MJB_MAX_AGENTS];
   int opos[MJB_MAX_AGENTS];
   if (is_reset)  // data_store = {agent: {}} (mujoco_rl.py:312); the draw counter is not part of the store
+    MJB_NOUNROLL
     for (int a = 0; a < A; a++) {
+      MJB_NOUNROLL
       for (int k = 0; k < dm.store_i32; k++) if (k != MJB_STORE_I_DRAWS) si[a * dm.store_i32 + k] = 0;
+      MJB_NOUNROLL
       for (int k = 0; k < dm.store_f32; k++) sf[a * dm.store_f32 + k] = 0.f;
     }
+  MJB_NOUNROLL
   for (int a = 0; a < A; a++) { reward[a] = 0.f; done[a] = false; opos[a] = dm.obs_adr[a + 1] - dm.obs_adr[a]; }
+  MJB_NOUNROLL
   for (int p = 0; p < dm.n_dynamics; p++) {
     const DevPlugin& dyn = dm.dynamics[p];
+    MJB_NOUNROLL
     for (int a = 0; a < A; a++) {
       int* sia = si + a * dm.store_i32;
       float* sfa = sf + a * dm.store_f32;
@@ -84,8 +90,11 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
   }
   if (is_reset) {
     // everything the dynamics wrote is discarded (mujoco_rl.py:326-328); rewards / dones are not run
+    MJB_NOUNROLL
     for (int a = 0; a < A; a++) {
+      MJB_NOUNROLL
       for (int k = 0; k < dm.store_i32; k++) if (k != MJB_STORE_I_DRAWS) si[a * dm.store_i32 + k] = 0;
+      MJB_NOUNROLL
       for (int k = 0; k < dm.store_f32; k++) sf[a * dm.store_f32 + k] = 0.f;
       rew[a] = 0.f; term[a] = 0; trunc[a] = 0;
     }
@@ -93,8 +102,10 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
     B.timestep[env] = 0;
     return;
   }
+  MJB_NOUNROLL
   for (int p = 0; p < dm.n_rewards; p++) {
     const DevPlugin& rf = dm.rewards[p];
+    MJB_NOUNROLL
     for (int a = 0; a < A; a++) {
       int* sia = si + a * dm.store_i32;
       float* sfa = sf + a * dm.store_f32;
@@ -116,6 +127,7 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
           sia[MJB_STORE_I_HAS_XPOS] = 1;
         } else {
           float cc = 0.f;
+          MJB_NOUNROLL
           for (int u = 0; u < dm.nu; u++) cc += SF(ctrl)[u] * SF(ctrl)[u];
           // contact cost term: cfrc_ext is zero on these models (no force/acc sensors), SURVEY Q11
           reward[a] += (x_after - sfa[MJB_STORE_F_XPOS_BEFORE]) / dm.timestep - 0.5f * cc;
@@ -126,14 +138,19 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
   }
   int ts = B.timestep[env];
   uint8_t tr = ts >= dm.max_steps ? 1 : 0;
+  MJB_NOUNROLL
   for (int a = 0; a <= A; a++) trunc[a] = tr;
   bool all = false;
+  MJB_NOUNROLL
   for (int p = 0; p < dm.n_dones && !all; p++) {
     const DevPlugin& df = dm.dones[p];
+    MJB_NOUNROLL
     for (int a = 0; a < A; a++)
       if (df.kind == MJB_DONE_DISTANCE_LE) done[a] = done[a] || (sf[a * dm.store_f32 + MJB_STORE_F_DISTANCE] <= df.param[0]);
+    MJB_NOUNROLL
     for (int a = 0; a < A; a++) all = all || done[a];
   }
+  MJB_NOUNROLL
   for (int a = 0; a < A; a++) { rew[a] = reward[a]; term[a] = done[a] ? 1 : 0; }
   term[A] = all ? 1 : 0;
   B.timestep[env] = ts + 1;
@@ -153,20 +170,29 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
   float* g_sens = B.sensordata + (size_t)env * dm.sensor_stride;
   float* g_probe = B.probe + (size_t)env * dm.nprobe * 4;
   if (mode == MODE_RESET) {
+    MJB_NOUNROLL
     for (int i = lane; i < dm.nq; i += 32) qpos[i] = CF(qpos0)[i];
+    MJB_NOUNROLL
     for (int i = lane; i < dm.nv; i += 32) { qvel[i] = 0.f; qacc[i] = 0.f; }
+    MJB_NOUNROLL
     for (int i = lane; i < dm.nu; i += 32) ctrl[i] = 0.f;
   } else {
+    MJB_NOUNROLL
     for (int i = lane; i < dm.nq; i += 32) qpos[i] = g_qpos[i];
+    MJB_NOUNROLL
     for (int i = lane; i < dm.nv; i += 32) { qvel[i] = g_qvel[i]; qacc[i] = g_warm[i]; }
+    MJB_NOUNROLL
     for (int i = lane; i < dm.nu; i += 32) ctrl[i] = g_ctrl[i];
   }
+  MJB_NOUNROLL
   for (int i = lane; i < dm.nsensordata; i += 32) sens[i] = mode == MODE_RESET ? 0.f : g_sens[i];
+  MJB_NOUNROLL
   for (int i = lane; i < 4 * dm.nprobe; i += 32) probe[i] = g_probe[i];
   MJB_SYNC();
   if (mode == MODE_STEP || mode == MODE_PHYSICS) {
     // apply_action (mujoco_parent.py:316-332): overwrite qvel (freeJoint) or ctrl
     const float* act = B.actions + (size_t)env * dm.n_agents * dm.act_stride;
+    MJB_NOUNROLL
     for (int i = lane; i < dm.n_agents * dm.n_phys_act; i += 32) {
       float v = act[(i / dm.n_phys_act) * dm.act_stride + (i % dm.n_phys_act)];
       int idx = CI(act_index)[i];
@@ -178,11 +204,13 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
   // mj_forward (reset / forward modes) is one pass of the same loop body without integration
   const bool integrate = !(mode == MODE_FORWARD || mode == MODE_RESET);
   const int passes = integrate ? skip_frames : 1;
+  MJB_NOUNROLL
   for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, nullptr);
   if (ncon >= 0) {
     if (B.ncon && lane == 0) B.ncon[env] = ncon;
     if (B.contact_geom) {
       const uint32_t* pairs = CU(pair_pack);
+      MJB_NOUNROLL
       for (int k = lane; k < dm.maxcon; k += 32) {
         int g1 = -1, g2 = -1;
         float dist = 0.f;
@@ -198,16 +226,23 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
     }
   }
   MJB_SYNC();
+  MJB_NOUNROLL
   for (int i = lane; i < dm.nq; i += 32) g_qpos[i] = qpos[i];
+  MJB_NOUNROLL
   for (int i = lane; i < dm.nv; i += 32) { g_qvel[i] = qvel[i]; g_warm[i] = qacc[i]; }
+  MJB_NOUNROLL
   for (int i = lane; i < dm.nu; i += 32) g_ctrl[i] = ctrl[i];
+  MJB_NOUNROLL
   for (int i = lane; i < dm.nsensordata; i += 32) g_sens[i] = sens[i];
+  MJB_NOUNROLL
   for (int i = lane; i < 4 * dm.nprobe; i += 32) g_probe[i] = probe[i];
   if (mode != MODE_STEP && mode != MODE_RESET) return;
   // ---- epilogue: get_observations (mujoco_parent.py:380-392): sensordata(t) ++ qpos(t+h) ++ qvel(t+h)
+  MJB_NOUNROLL
   for (int a = 0; a < dm.n_agents; a++) {
     float* oa = B.obs + ((size_t)env * dm.n_agents + a) * dm.obs_stride;
     int n = dm.obs_adr[a + 1] - dm.obs_adr[a];
+    MJB_NOUNROLL
     for (int i = lane; i < n; i += 32) {
       int e = CI(obs_index)[dm.obs_adr[a] + i], kind = e >> 24, adr = e & 0xffffff;
       oa[i] = kind == 0 ? sens[adr] : (kind == 1 ? qpos[adr] : qvel[adr]);

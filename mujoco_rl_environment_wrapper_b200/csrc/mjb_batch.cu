@@ -44,7 +44,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // One CTA per SM slot, `warps` environments in flight per CTA; each warp walks the env index space
 // with a grid-wide stride (envs are independent, no inter-warp communication after the staging).
 __global__ void k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
-                      int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask) {
+                      int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env) {
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* img = smem + 4;  // 16 B after the barrier
@@ -63,9 +63,15 @@ __global__ void k_env(const __grid_constant__ DevModel dm, const uint32_t* __res
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
   Ctx c{&dm, img, scratch, lane, probe};
-  for (int env = blockIdx.x * warps + warp; env < num_envs; env += gridDim.x * warps) {
+  // dynamic env scheduling: per-env cost varies (contact count, Newton iterations), so every warp pulls
+  // its next env from a grid-wide counter instead of owning a fixed slice
+  int env = blockIdx.x * warps + warp;
+  while (env < num_envs) {
     run_env(c, B, env, mode, skip_frames, mask);
     __syncwarp();
+    int nxt = 0;
+    if (lane == 0) nxt = atomicAdd(next_env, 1);
+    env = __shfl_sync(0xffffffffu, nxt, 0);
   }
 }
 
@@ -78,10 +84,13 @@ struct mjb_batch {
   size_t smem_bytes = 0;
   cudaStream_t stream = nullptr;
   uint32_t* d_image = nullptr;
+  int* d_next = nullptr;   // ring of work counters, one per in-flight launch
+  int next_slot = 0;
   int64_t launches = 0;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
   // pinned staging for the host-buffer entry point
+  int* h_first = nullptr;  // pinned: initial value of the work counter (= grid * warps)
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
 };
@@ -103,8 +112,14 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, b->stream));
   }
+  // the first grid*warps envs are taken statically; the counter hands out the rest
+  int first = b->grid * b->warps;
+  int* counter = b->d_next + b->next_slot;
+  b->next_slot = (b->next_slot + 1) % 64;
+  CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  (void)first;
   mjb::k_env<<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode,
-                                                                     skip_frames, mask);
+                                                                     skip_frames, mask, counter);
   CUDA_TRY(cudaGetLastError());
   if (b->timing) {
     CUDA_TRY(cudaEventRecord(e1, b->stream));
@@ -190,6 +205,11 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     mjb::set_error("device image upload failed");
     return fail(MJB_ERR_CUDA);
   }
+  if (cudaMalloc(&b->d_next, 64 * sizeof(int)) != cudaSuccess || cudaMallocHost(&b->h_first, sizeof(int)) != cudaSuccess) {
+    mjb::set_error("work counter allocation failed");
+    return fail(MJB_ERR_CUDA);
+  }
+  b->h_first[0] = b->grid * b->warps;
   const int A = dm.n_agents;
   if (cudaMallocHost(&b->h_act, sizeof(float) * (size_t)num_envs * A * dm.act_stride + 16) != cudaSuccess ||
       cudaMallocHost(&b->h_obs, sizeof(float) * (size_t)num_envs * A * dm.obs_stride + 16) != cudaSuccess ||
@@ -207,6 +227,8 @@ void mjb_batch_destroy(mjb_batch* b) {
   if (!b) return;
   for (auto& ev : b->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (b->d_image) cudaFree(b->d_image);
+  if (b->d_next) cudaFree(b->d_next);
+  if (b->h_first) cudaFreeHost(b->h_first);
   if (b->h_act) cudaFreeHost(b->h_act);
   if (b->h_obs) cudaFreeHost(b->h_obs);
   if (b->h_rew) cudaFreeHost(b->h_rew);

@@ -111,7 +111,9 @@ MJB_DEV void fk(const Ctx& c) {
   const int* level_adr = CI(level_adr);
   float* qpos = SF(qpos);
   float *xpos = SF(xpos), *xquat = SF(xquat), *xmat = SF(xmat), *xipos = SF(xipos), *cdof = SF(cdof);
+  MJB_NOUNROLL
   for (int l = 0; l < dm.nlevel; l++) {
+    MJB_NOUNROLL
     for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
       int p = CI(mb_parent)[b], root = CI(mb_root)[b];
       f3 pos = ld3(CF(mb_pos) + 3 * b);
@@ -121,6 +123,7 @@ MJB_DEV void fk(const Ctx& c) {
         quat = qmul(ldq(xquat + 4 * p), quat);
       }
       int ja = CI(mb_jntadr)[b], jn = CI(mb_jntnum)[b];
+      MJB_NOUNROLL
       for (int j = ja; j < ja + jn; j++) {
         int type = CI(jnt_type)[j], qa = CI(jnt_qposadr)[j], da = CI(jnt_dofadr)[j];
         if (type == MJB_JNT_FREE) {
@@ -150,6 +153,7 @@ MJB_DEV void fk(const Ctx& c) {
       for (int i = 0; i < 9; i++) xmat[9 * b + i] = R[i];
       st3(xipos + 3 * b, pos + mulv(R, ld3(CF(mb_ipos) + 3 * b)));
       f3 o = (root == b) ? pos : ld3(xpos + 3 * root);
+      MJB_NOUNROLL
       for (int j = ja; j < ja + jn; j++) {
         int type = CI(jnt_type)[j], da = CI(jnt_dofadr)[j];
         if (type == MJB_JNT_FREE) {
@@ -173,6 +177,7 @@ MJB_DEV void fk(const Ctx& c) {
   }
   // body inertias about the tree origin
   float* cinert = SF(cinert);
+  MJB_NOUNROLL
   for (int b = c.lane; b < dm.nmb; b += 32) {
     float R[9];
     q2m(qmul(ldq(xquat + 4 * b), ldq(CF(mb_iquat) + 4 * b)), R);
@@ -190,6 +195,7 @@ MJB_DEV void fk(const Ctx& c) {
   }
   // dynamic geom frames
   float *gpos = SF(gpos), *gmat = SF(gmat);
+  MJB_NOUNROLL
   for (int g = c.lane; g < dm.ngeom; g += 32) {
     int slot = CI(geom_slot)[g];
     if (slot < 0) continue;
@@ -198,6 +204,7 @@ MJB_DEV void fk(const Ctx& c) {
     q2m(qmul(ldq(xquat + 4 * b), ldq(CF(geom_quat) + 4 * g)), gmat + 9 * slot);
   }
   float *spos = SF(spos), *smat = SF(smat);
+  MJB_NOUNROLL
   for (int t = c.lane; t < dm.nsite; t += 32) {
     int b = CI(site_mb)[t];
     f3 lp = ld3(CF(site_pos) + 3 * t);
@@ -214,16 +221,21 @@ MJB_DEV void crb_mass(const Ctx& c) {
   const DevModel& dm = *c.dm;
   const int* level_adr = CI(level_adr);
   float *cinert = SF(cinert), *crb = SF(crb), *M = SF(M), *cdof = SF(cdof);
+  MJB_NOUNROLL
   for (int i = c.lane; i < 10 * dm.nmb; i += 32) crb[i] = cinert[i];
+  MJB_NOUNROLL
   for (int i = c.lane; i < (dm.nv * (dm.nv + 1)) / 2; i += 32) M[i] = 0.f;
   MJB_SYNC();
+  MJB_NOUNROLL
   for (int l = dm.nlevel - 2; l >= 0; l--) {
+    MJB_NOUNROLL
     for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
       int ca = CI(mb_childadr)[b], ce = CI(mb_childadr)[b + 1];
       if (ce > ca) {
         float acc[10];
 #pragma unroll
         for (int i = 0; i < 10; i++) acc[i] = crb[10 * b + i];
+        MJB_NOUNROLL
         for (int k = ca; k < ce; k++) {
           int ch = CI(mb_child)[k];
 #pragma unroll
@@ -235,6 +247,7 @@ MJB_DEV void crb_mass(const Ctx& c) {
     }
     MJB_SYNC();
   }
+  MJB_NOUNROLL
   for (int i = c.lane; i < dm.nv; i += 32) {
     int b = CI(dof_mb)[i];
     f3 n, f;
@@ -256,7 +269,9 @@ MJB_DEV void rne_pass(const Ctx& c, bool with_acc) {
   const int* level_adr = CI(level_adr);
   float *cdof = SF(cdof), *cvel = SF(cvel), *cacc = SF(cacc), *qvel = SF(qvel), *qacc = SF(qacc);
   float *cinert = SF(cinert), *cfrc = SF(crb);  // crb is dead after crb_mass: reuse as body force
+  MJB_NOUNROLL
   for (int l = 0; l < dm.nlevel; l++) {
+    MJB_NOUNROLL
     for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
       int p = CI(mb_parent)[b];
       f3 w = mk3(0, 0, 0), v = mk3(0, 0, 0), aw = mk3(0, 0, 0);
@@ -264,6 +279,7 @@ MJB_DEV void rne_pass(const Ctx& c, bool with_acc) {
       if (p >= 0) { w = ld3(cvel + 6 * p); v = ld3(cvel + 6 * p + 3); aw = ld3(cacc + 6 * p); av = ld3(cacc + 6 * p + 3); }
       int da = CI(mb_dofadr)[b], dn = CI(mb_dofnum)[b];
       f3 wb = w, vb = v;  // velocity snapshot for the free joint's rotational block
+      MJB_NOUNROLL
       for (int d = da; d < da + dn; d++) {
         int kind = CI(dof_kind)[d];
         f3 sw = ld3(cdof + 6 * d), sv = ld3(cdof + 6 * d + 3);
@@ -292,9 +308,12 @@ MJB_DEV void rne_pass(const Ctx& c, bool with_acc) {
     MJB_SYNC();
   }
   if (with_acc) return;
+  MJB_NOUNROLL
   for (int l = dm.nlevel - 2; l >= 0; l--) {
+    MJB_NOUNROLL
     for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
       int ca = CI(mb_childadr)[b], ce = CI(mb_childadr)[b + 1];
+      MJB_NOUNROLL
       for (int k = ca; k < ce; k++) {
         int ch = CI(mb_child)[k];
 #pragma unroll
@@ -304,10 +323,12 @@ MJB_DEV void rne_pass(const Ctx& c, bool with_acc) {
     MJB_SYNC();
   }
   float *qfrc = SF(qfrc), *ctrl = SF(ctrl);
+  MJB_NOUNROLL
   for (int d = c.lane; d < dm.nv; d += 32) {
     int b = CI(dof_mb)[d];
     float bias = dot(ld3(cdof + 6 * d), ld3(cfrc + 10 * b)) + dot(ld3(cdof + 6 * d + 3), ld3(cfrc + 10 * b + 3));
     float f = -CF(dof_damping)[d] * qvel[d] - bias;
+    MJB_NOUNROLL
     for (int u = 0; u < dm.nu; u++)
       if (CI(act_dof)[u] == d) {
         const float* ap = CF(act_param) + 4 * u;
@@ -387,6 +408,7 @@ MJB_DEV int capsule_box(const GeomW& g1, const GeomW& g2, float margin, ConOut* 
   const float gr = 0.6180339887f;
   float x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
   float f1 = point_box_dist(a + ab * x1, g2.size), f2 = point_box_dist(a + ab * x2, g2.size);
+  MJB_NOUNROLL
   for (int it = 0; it < 40; it++) {
     if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = point_box_dist(a + ab * x1, g2.size); }
     else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = point_box_dist(a + ab * x2, g2.size); }
@@ -417,10 +439,12 @@ MJB_DEV int capsule_capsule(const GeomW& g1, const GeomW& g2, float margin, ConO
     return sphere_sphere(g1.pos + a1 * x1, r1, g2.pos + a2 * x2, r2, margin, o[0]);
   }
   int k = 0;
+  MJB_NOUNROLL
   for (int e = 0; e < 2 && k < 2; e++) {
     float x1 = e == 0 ? len1 : -len1, x2 = fminf(len2, fmaxf(-len2, v - mb * x1));
     k += sphere_sphere(g1.pos + a1 * x1, r1, g2.pos + a2 * x2, r2, margin, o[k]);
   }
+  MJB_NOUNROLL
   for (int e = 0; e < 2 && k < 2; e++) {
     float x2 = e == 0 ? len2 : -len2, x1 = u - mb * x2;
     if (x1 > len1 || x1 < -len1) continue;
@@ -458,6 +482,7 @@ MJB_DEV int collide(const Ctx& c) {
   int* cand = SI(cand);
   int ncand = 0;
   // broad phase: bounding spheres (planes: signed distance of the centre)
+  MJB_NOUNROLL
   for (int base = 0; base < dm.npair; base += 32) {
     int p = base + c.lane;
     bool keep = false;
@@ -486,6 +511,7 @@ MJB_DEV int collide(const Ctx& c) {
   MJB_SYNC();
   // narrow phase, lane = candidate (types with at most two contacts)
   int ncon = 0;
+  MJB_NOUNROLL
   for (int base = 0; base < ncand; base += 32) {
     int i = base + c.lane;
     int n = 0, p = -1;
@@ -528,6 +554,7 @@ MJB_DEV int collide(const Ctx& c) {
     }
   }
   // multi-contact types (plane-box, box-box): one candidate at a time, lane = box corner
+  MJB_NOUNROLL
   for (int i = 0; i < ncand; i++) {
     int p = cand[i];
     uint32_t pk = pairs[p];
@@ -608,6 +635,7 @@ MJB_DEV float impedance(const float* solimp, float pos, float margin) {
 MJB_DEV void make_constraints(const Ctx& c, int ncon) {
   const DevModel& dm = *c.dm;
   float *efcD = SF(efcD), *efcAref = SF(efcAref), *qpos = SF(qpos), *qvel = SF(qvel);
+  MJB_NOUNROLL
   for (int k = c.lane; k < dm.nlim; k += 32) {
     const float* lp = CF(lim_param) + LIM_STRIDE * k;
     float q = qpos[CI(lim_qposadr)[k]], v = qvel[CI(lim_dof)[k]];
@@ -628,12 +656,14 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
   // contact Jacobians: lane = dof, rows (normal, tangent1, tangent2) per contact
   float *J = SF(J), *con = SF(con), *cdof = SF(cdof), *xpos = SF(xpos);
   const uint32_t* pairs = CU(pair_pack);
+  MJB_NOUNROLL
   for (int d = c.lane; d < dm.nv; d += 32) {
     f3 sw = ld3(cdof + 6 * d), sv = ld3(cdof + 6 * d + 3);
     int root = CI(mb_root)[CI(dof_mb)[d]];
     f3 o = ld3(xpos + 3 * root);
     uint32_t bit = 1u << (d & 31);
     int word = d >> 5;
+    MJB_NOUNROLL
     for (int k = 0; k < ncon; k++) {
       const float* r = con + CON_STRIDE * k;
       uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
@@ -652,6 +682,7 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
   MJB_SYNC();
   // per-contact regulariser and reference acceleration: lane = contact
   int base = 2 * dm.nlim;
+  MJB_NOUNROLL
   for (int k = c.lane; k < ncon; k += 32) {
     const float* r = con + CON_STRIDE * k;
     uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
@@ -661,6 +692,7 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
     float mu = pc[PC_MU], dist = r[CON_DIST], inc = pc[PC_INCMARGIN];
     float imp = impedance(pc + PC_SOLIMP, dist, inc);
     float vn = 0.f, v1 = 0.f, v2 = 0.f;
+    MJB_NOUNROLL
     for (int d = 0; d < dm.nv; d++) {
       float qd = qvel[d];
       vn += J[(3 * k) * dm.ldj + d] * qd; v1 += J[(3 * k + 1) * dm.ldj + d] * qd; v2 += J[(3 * k + 2) * dm.ldj + d] * qd;
@@ -690,8 +722,11 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
 MJB_DEV float matvec_row(const float* A, const float* x, int row, int t0, int t1) {
   float s0 = 0.f, s1 = 0.f;
   int j = t0;
+  MJB_NOUNROLL
   for (; j + 1 <= row && j + 1 < t1; j += 2) { s0 += A[tri(row, j)] * x[j]; s1 += A[tri(row, j + 1)] * x[j + 1]; }
+  MJB_NOUNROLL
   for (; j <= row && j < t1; j++) s0 += A[tri(row, j)] * x[j];
+  MJB_NOUNROLL
   for (; j < t1; j++) s1 += A[tri(j, row)] * x[j];
   return s0 + s1;
 }
@@ -700,6 +735,7 @@ MJB_DEV float matvec_row(const float* A, const float* x, int row, int t0, int t1
 MJB_DEV float cholesky(float* A, int lane, int t0, int t1, int nb) {
   float invd = 1.f;
   const bool own = lane < t1;  // lanes >= nv have t0 = t1 = 0
+  MJB_NOUNROLL
   for (int jj = 0; jj < nb; jj++) {
     const int j = t0 + jj;
     const bool col = own && j < t1;
@@ -709,6 +745,7 @@ MJB_DEV float cholesky(float* A, int lane, int t0, int t1, int nb) {
       const float* ri = A + tri(lane, 0);
       const float* rj = A + tri(j, 0);
       int k = t0;
+      MJB_NOUNROLL
       for (; k + 1 < j; k += 2) { s0 -= ri[k] * rj[k]; s1 -= ri[k + 1] * rj[k + 1]; }
       if (k < j) s0 -= ri[k] * rj[k];
     }
@@ -727,6 +764,7 @@ MJB_DEV float cholesky(float* A, int lane, int t0, int t1, int nb) {
 MJB_DEV float chol_solve(const float* A, int lane, int t0, int t1, int nb, float invd, float b) {
   float x = b;
   const bool own = lane < t1;
+  MJB_NOUNROLL
   for (int kk = 0; kk < nb; kk++) {
     const int k = t0 + kk;
     const bool col = own && k < t1;
@@ -736,6 +774,7 @@ MJB_DEV float chol_solve(const float* A, int lane, int t0, int t1, int nb, float
       else if (lane > k) x -= A[tri(lane, k)] * yk;
     }
   }
+  MJB_NOUNROLL
   for (int kk = nb - 1; kk >= 0; kk--) {
     const int k = t0 + kk;
     const bool col = own && k < t1;
@@ -751,6 +790,7 @@ MJB_DEV float chol_solve(const float* A, int lane, int t0, int t1, int nb, float
 // jar-like product for every row: out[row] = J_row . x   (limit rows: +-x[dof]; contact rows: pyramid edges)
 MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const float* sub) {
   const DevModel& dm = *c.dm;
+  MJB_NOUNROLL
   for (int k = c.lane; k < dm.nlim; k += 32) {
     float v = x[CI(lim_dof)[k]];
     out[2 * k] = v - (sub ? sub[2 * k] : 0.f);
@@ -759,15 +799,18 @@ MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const 
   const float* J = SF(J);
   const float* con = SF(con);
   int base = 2 * dm.nlim;
+  MJB_NOUNROLL
   for (int r = c.lane; r < 3 * ncon; r += 32) {
     float s0 = 0.f, s1 = 0.f;
     const float* jr = J + r * dm.ldj;
     int d = 0;
+    MJB_NOUNROLL
     for (; d + 1 < dm.nv; d += 2) { s0 += jr[d] * x[d]; s1 += jr[d + 1] * x[d + 1]; }
     if (d < dm.nv) s0 += jr[d] * x[d];
     out[base + 4 * (r / 3) + (r % 3)] = s0 + s1;
   }
   MJB_SYNC();
+  MJB_NOUNROLL
   for (int k = c.lane; k < ncon; k += 32) {
     float mu = con[CON_STRIDE * k + CON_MU];
     float n = out[base + 4 * k], t1 = out[base + 4 * k + 1], t2 = out[base + 4 * k + 2];
@@ -795,11 +838,13 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
   rows_mul(c, ncon, a, jar, aref);
   int it = 0;
   bool stalled = false;
+  MJB_NOUNROLL
   for (;; it++) {
     // gradient = M a - qfrc_smooth - J' f
     float g = 0.f;
     if (lane < nv) {
       g = Ma[lane] - qfrc[lane];
+      MJB_NOUNROLL
       for (int k = 0; k < ncon; k++) {
         float mu = con[CON_STRIDE * k + CON_MU];
         float f0 = jar[base + 4 * k] < 0 ? -D[base + 4 * k] * jar[base + 4 * k] : 0.f;
@@ -812,6 +857,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       grad[lane] = g;
     }
     MJB_SYNC();
+    MJB_NOUNROLL
     for (int k = lane; k < dm.nlim; k += 32) {
       float flo = jar[2 * k] < 0 ? -D[2 * k] * jar[2 * k] : 0.f, fhi = jar[2 * k + 1] < 0 ? -D[2 * k + 1] * jar[2 * k + 1] : 0.f;
       grad[CI(lim_dof)[k]] -= flo - fhi;
@@ -822,14 +868,17 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     float fn = wsum(lane < nv ? qfrc[lane] * qfrc[lane] + Ma[lane] * Ma[lane] : 0.f);
     if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) break;
     // Hessian H = M + J' diag(D active) J (packed lower triangle)
+    MJB_NOUNROLL
     for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) H[i] = M[i];
     MJB_SYNC();
+    MJB_NOUNROLL
     for (int k = lane; k < dm.nlim; k += 32) {
       int d = CI(lim_dof)[k];
       H[tri(d, d)] += (jar[2 * k] < 0 ? D[2 * k] : 0.f) + (jar[2 * k + 1] < 0 ? D[2 * k + 1] : 0.f);
     }
     MJB_SYNC();
     bool coupled = false;  // does an active contact couple two kinematic trees?
+    MJB_NOUNROLL
     for (int k = 0; k < ncon; k++) {
       uint32_t pk = pairs[((const int*)(con + CON_STRIDE * k))[CON_PAIR]];
       int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
@@ -847,6 +896,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       // row i (lane) x column j (set bits of mask, j <= i)
       float ri_n = cnn * jn + cn1 * j1 + cn2 * j2, ri_1 = cn1 * jn + c11 * j1, ri_2 = cn2 * jn + c22 * j2;
       uint32_t mm = mask;
+      MJB_NOUNROLL
       while (mm) {
         int j = MJB_FFS(mm) - 1;
         mm &= mm - 1;
@@ -868,8 +918,10 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     float p2 = wsum(lane < nv ? s * mv : 0.f);
     // exact line search on the convex piecewise-quadratic phi(alpha): safeguarded Newton on phi'
     float alpha = 0.f, lo = 0.f, hi = MJB_BIG, d1_0 = 0.f;
+    MJB_NOUNROLL
     for (int ls = 0; ls <= dm.ls_iterations; ls++) {
       float d1 = 0.f, d2 = 0.f;
+      MJB_NOUNROLL
       for (int r = lane; r < nrow; r += 32) {
         float x = jar[r] + alpha * jv[r];
         if (x < 0.f) { d1 += D[r] * x * jv[r]; d2 += D[r] * jv[r] * jv[r]; }
@@ -889,6 +941,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     float amax = wmax(lane < nv ? fabsf(a[lane]) : 0.f), smax = wmax(fabsf(alpha * s));
     stalled = smax <= 1e-7f * (1.f + amax);
     if (lane < nv) { a[lane] += alpha * s; Ma[lane] += alpha * mv; }
+    MJB_NOUNROLL
     for (int r = lane; r < nrow; r += 32) jar[r] += alpha * jv[r];
     MJB_SYNC();
   }
@@ -963,12 +1016,14 @@ MJB_DEV float cutoff(const Ctx& c, int i, float x) {
 MJB_DEV void sensors_pos(const Ctx& c) {
   const DevModel& dm = *c.dm;
   float* sens = SF(sens);
+  MJB_NOUNROLL
   for (int i = 0; i < dm.nsensor; i++) {
     int type = CI(sensor_type)[i], t = CI(sensor_site)[i], adr = CI(sensor_adr)[i];
     if (type == MJB_SENS_RANGEFINDER) {
       f3 pnt = ld3(SF(spos) + 3 * t), vec = colv(SF(smat) + 9 * t, 2);
       int bex = CI(site_mb)[t];
       float best = MJB_BIG;
+      MJB_NOUNROLL
       for (int g = c.lane; g < dm.ngeom; g += 32) {
         int gb = CI(geom_mb)[g];
         if ((gb >= 0 && gb == bex) || !CI(geom_ray)[g]) continue;
@@ -993,11 +1048,13 @@ MJB_DEV void sensors_acc(const Ctx& c, int ncon) {
   bool did_rne = false;
   const uint32_t* pairs = CU(pair_pack);
   const int base = 2 * dm.nlim;
+  MJB_NOUNROLL
   for (int i = 0; i < dm.nsensor; i++) {
     int type = CI(sensor_type)[i], t = CI(sensor_site)[i], adr = CI(sensor_adr)[i];
     if (type == MJB_SENS_TOUCH) {
       int body = CI(site_mb)[t];
       float total = 0.f;
+      MJB_NOUNROLL
       for (int k = c.lane; k < ncon; k += 32) {
         const float* r = SF(con) + CON_STRIDE * k;
         uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
@@ -1042,6 +1099,7 @@ MJB_DEV int forward(const Ctx& c, bool sensors, int* iters_out) {
     // exported positions belong to THIS forward pass, i.e. to the state before the integration that
     // follows; taken now because xipos is recycled by the solver scratch below
     const DevModel& dm = *c.dm;
+    MJB_NOUNROLL
     for (int p = c.lane; p < dm.nprobe; p += 32) {
       int kind = CI(probe_kind)[p], id = CI(probe_id)[p];
       f3 v = kind == PROBE_BODY ? ld3(SF(xipos) + 3 * id) : (kind == PROBE_GEOM ? ld3(SF(gpos) + 3 * id) : ld3(CF(probe_const) + 3 * p));
@@ -1063,6 +1121,7 @@ MJB_DEV int forward(const Ctx& c, bool sensors, int* iters_out) {
 // qpos += h * qvel-like `v` (lane = joint)
 MJB_DEV void integrate_pos(const Ctx& c, float* qpos, const float* v, float h) {
   const DevModel& dm = *c.dm;
+  MJB_NOUNROLL
   for (int j = c.lane; j < dm.njnt; j += 32) {
     int qa = CI(jnt_qposadr)[j], da = CI(jnt_dofadr)[j];
     if (CI(jnt_type)[j] == MJB_JNT_FREE) {
@@ -1094,6 +1153,7 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) 
   float* rk = SF(rk);
   float *q0 = rk, *v0 = rk + dm.nq, *dq = rk + dm.nq + nv, *dv = rk + dm.nq + 2 * nv;
   int ncon = 0;
+  MJB_NOUNROLL
   for (int st = 0; st < nstage; st++) {
     if (st > 0) {
       // stage state: q = q0 (+) h A x_{st-1}.v ; v = v0 + h A f_{st-1}   (A = 1/2, 1/2, 1)
@@ -1101,6 +1161,7 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) 
       float vprev = lane < nv ? qvel[lane] : 0.f, aprev = lane < nv ? qacc[lane] : 0.f;
       MJB_SYNC();
       if (lane < nv) SF(vecC)[lane] = A * vprev;
+      MJB_NOUNROLL
       for (int i = lane; i < dm.nq; i += 32) qpos[i] = q0[i];
       MJB_SYNC();
       integrate_pos(c, qpos, SF(vecC), h);
@@ -1111,6 +1172,7 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) 
     if (rk4) {
       const float Bw = (st == 0 || st == 3) ? (1.f / 6) : (1.f / 3);
       if (st == 0) {
+        MJB_NOUNROLL
         for (int i = lane; i < dm.nq; i += 32) q0[i] = qpos[i];
         if (lane < nv) { v0[lane] = qvel[lane]; dq[lane] = 0.f; dv[lane] = 0.f; }
       }
@@ -1121,6 +1183,7 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) 
   if (!integrate) return ncon;
   if (rk4) {
     if (lane < nv) qvel[lane] = v0[lane] + h * dv[lane];
+    MJB_NOUNROLL
     for (int i = lane; i < dm.nq; i += 32) qpos[i] = q0[i];
     MJB_SYNC();
     integrate_pos(c, qpos, dq, h);
@@ -1132,6 +1195,7 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) 
     // (M + h D) a' = qfrc_smooth + qfrc_constraint  ( = M a - gradient at the solver's exit point)
     float *M = SF(M), *H = SF(H);
     const int t0 = CI(dof_t0)[lane], t1 = CI(dof_t1)[lane];
+    MJB_NOUNROLL
     for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) H[i] = M[i];
     MJB_SYNC();
     if (lane < nv) H[tri(lane, lane)] += h * CF(dof_damping)[lane];

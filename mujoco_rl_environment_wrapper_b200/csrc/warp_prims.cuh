@@ -11,6 +11,7 @@
 #include "../../tests/emu/simt_emu.h"
 #define MJB_DEV inline
 #define MJB_DEV_NOINLINE inline
+#define MJB_NOUNROLL
 #define MJB_LANE() (simt::lane())
 #define MJB_SYNC() simt::barrier()
 #define MJB_SHFL(v, src) simt::shfl((v), (src))
@@ -22,6 +23,7 @@
 #else
 #define MJB_DEV __device__ __forceinline__
 #define MJB_DEV_NOINLINE __device__ __noinline__
+#define MJB_NOUNROLL _Pragma("unroll 1")
 #define MJB_LANE() ((int)(threadIdx.x & 31))
 #define MJB_SYNC() __syncwarp()
 #define MJB_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))

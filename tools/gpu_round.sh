@@ -4,12 +4,14 @@ set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
 python __graft_entry__.py smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log
-python bench.py --steps 100 --warmup 10 2> gpurun_out/bench.err | tee gpurun_out/bench.json
-export MJB_BENCH_SETTLE=40
+python bench.py --steps 100 --warmup 10 ${BENCH_FLAGS} 2> gpurun_out/bench.err | tee gpurun_out/bench.json
+if [ "${SKIP_NCU}" != "1" ]; then
+export MJB_BENCH_SETTLE=300
 python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 290 -c 40 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1
 python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_env -s 44 -c 2 -o gpurun_out/prof -f \
+ncu --set full --clock-control none --import-source on -k regex:k_env -s 304 -c 1 -o gpurun_out/prof -f \
     python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
+fi
 ls -la gpurun_out
