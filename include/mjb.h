@@ -142,6 +142,7 @@ typedef struct mjb_buffers {
   int32_t* ncon;     /* [N] or NULL */
   int32_t* contact_geom; /* [N, maxcon, 2] or NULL */
   float* contact_dist;   /* [N, maxcon] or NULL */
+  int32_t* niter;        /* [N] or NULL: Newton iterations of the last forward pass (diagnostic) */
 } mjb_buffers;
 
 /* data_store column ids */

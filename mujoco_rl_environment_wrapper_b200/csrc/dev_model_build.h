@@ -88,7 +88,10 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   dm.ldm = m.nv | 1; dm.ldj = m.nv | 1;
   dm.solver_iterations = spec.solver_iterations > 0 ? spec.solver_iterations : env_int("MJB_SOLVER_ITERS", 24);
   dm.ls_iterations = spec.ls_iterations > 0 ? spec.ls_iterations : env_int("MJB_LS_ITERS", 12);
-  dm.solver_tol = 1e-6f;
+  {
+    const char* ts = getenv("MJB_SOLVER_TOL");
+    dm.solver_tol = (ts && *ts) ? (float)atof(ts) : 1e-6f;
+  }
 
   w.begin(IF_level_adr); for (int v : level_adr) w.i(v);
   w.begin(IF_mb_parent); for (int k = 0; k < nmb; k++) w.i(b2k[m.body_parentid[korder[k]]]);

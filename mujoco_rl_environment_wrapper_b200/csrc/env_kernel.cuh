@@ -204,10 +204,12 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
   // mj_forward (reset / forward modes) is one pass of the same loop body without integration
   const bool integrate = !(mode == MODE_FORWARD || mode == MODE_RESET);
   const int passes = integrate ? skip_frames : 1;
+  int niter = 0;
   MJB_NOUNROLL
-  for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, nullptr);
+  for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, &niter);
   if (ncon >= 0) {
     if (B.ncon && lane == 0) B.ncon[env] = ncon;
+    if (B.niter && lane == 0) B.niter[env] = niter;
     if (B.contact_geom) {
       const uint32_t* pairs = CU(pair_pack);
       MJB_NOUNROLL

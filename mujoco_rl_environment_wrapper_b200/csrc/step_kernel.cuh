@@ -787,6 +787,77 @@ MJB_DEV float chol_solve(const float* A, int lane, int t0, int t1, int nb, float
   return x;
 }
 
+// Register-resident variant for blocks of at most MJB_NB rows (every level of the reference: 14 dofs per
+// ant): lane i keeps row i of its block in registers, row j is broadcast with shuffles, no shared-memory
+// traffic and no barriers inside the factorisation.  Solves (A + diag) x = b for the lane's block where A is
+// a packed lower triangle in shared memory; L is written to `Lout` (packed) for the backward substitution.
+#define MJB_NB 16
+MJB_DEV_NOINLINE float factor_solve_reg(const float* A, float* Lout, int lane, int t0, int t1, int nb, float diag_add, float b) {
+  float a[MJB_NB];
+  const bool own = lane < t1;
+  const int li = lane - t0;
+#pragma unroll
+  for (int k = 0; k < MJB_NB; k++) {
+    a[k] = (own && k <= li && k < nb) ? A[tri(lane, t0 + k)] : 0.f;
+    if (k == li) a[k] += diag_add;
+  }
+  float invd = 1.f;
+#pragma unroll
+  for (int j = 0; j < MJB_NB; j++) {
+    if (j < nb) {
+      const int src = (t0 + j < t1) ? t0 + j : lane;
+      float s = a[j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= a[k] * MJB_SHFL(a[k], src);
+      float sj = MJB_SHFL(s, src);
+      float inv = MJB_RSQRT(fmaxf(sj, 1e-20f));
+      if (li == j) { invd = inv; a[j] = sj * inv; }
+      else if (li > j) a[j] = s * inv;
+    }
+  }
+  // keep L for the transposed solve
+#pragma unroll
+  for (int k = 0; k < MJB_NB; k++)
+    if (own && k <= li && k < nb) Lout[tri(lane, t0 + k)] = a[k];
+  // forward substitution from registers
+  float x = b;
+#pragma unroll
+  for (int k = 0; k < MJB_NB; k++) {
+    if (k < nb) {
+      const int src = (t0 + k < t1) ? t0 + k : lane;
+      float yk = MJB_SHFL(x * invd, src);
+      if (li == k) x = yk;
+      else if (li > k && own) x -= a[k] * yk;
+    }
+  }
+  MJB_SYNC();
+  // backward substitution: column k of L is row-contiguous in the packed store
+  MJB_NOUNROLL
+  for (int kk = nb - 1; kk >= 0; kk--) {
+    const int k = t0 + kk;
+    const bool col = own && k < t1;
+    float xk = MJB_SHFL(x * invd, col ? k : lane);
+    if (col) {
+      if (lane == k) x = xk;
+      else if (lane < k) x -= Lout[tri(k, lane)] * xk;
+    }
+  }
+  return x;
+}
+// (A + diag) x = b per block; picks the register path when the blocks are small enough
+MJB_DEV float factor_solve(const float* A, float* L, int lane, int t0, int t1, int nb, float diag_add, float b, int nv) {
+  if (nb <= MJB_NB) return factor_solve_reg(A, L, lane, t0, t1, nb, diag_add, b);
+  if (A != L) {
+    MJB_NOUNROLL
+    for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) L[i] = A[i];
+    MJB_SYNC();
+  }
+  if (lane < t1 && diag_add != 0.f) L[tri(lane, lane)] += diag_add;
+  MJB_SYNC();
+  float invd = cholesky(L, lane, t0, t1, nb);
+  return chol_solve(L, lane, t0, t1, nb, invd, b);
+}
+
 // jar-like product for every row: out[row] = J_row . x   (limit rows: +-x[dof]; contact rows: pyramid edges)
 MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const float* sub) {
   const DevModel& dm = *c.dm;
@@ -834,7 +905,13 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
   const float* con = SF(con);
   const uint32_t* pairs = CU(pair_pack);
   const int base = 2 * dm.nlim, nrow = base + 4 * ncon;
-  if (lane < nv) Ma[lane] = matvec_row(M, a, lane, t0, t1);
+  // start from the unconstrained acceleration a0 = M^-1 qfrc_smooth (fewer Newton iterations than the
+  // previous step's qacc under fast-changing controls, and exact when no constraint row is active)
+  {
+    float x = factor_solve(M, H, lane, t0, t1, dm.maxtree, 0.f, lane < nv ? qfrc[lane] : 0.f, nv);
+    if (lane < nv) { a[lane] = x; Ma[lane] = qfrc[lane]; }
+    MJB_SYNC();
+  }
   rows_mul(c, ncon, a, jar, aref);
   int it = 0;
   bool stalled = false;
@@ -907,8 +984,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     MJB_SYNC();
     // factor per tree block unless a contact couples trees (then one block over all dofs)
     const int h0 = coupled ? 0 : t0, h1 = coupled ? (lane < nv ? nv : 0) : t1, hb = coupled ? nv : dm.maxtree;
-    float invd = cholesky(H, lane, h0, h1, hb);
-    float s = chol_solve(H, lane, h0, h1, hb, invd, lane < nv ? -g : 0.f);
+    float s = factor_solve(H, H, lane, h0, h1, hb, 0.f, lane < nv ? -g : 0.f, nv);
     if (lane < nv) sv[lane] = s;
     MJB_SYNC();
     float mv = 0.f;
@@ -1195,14 +1271,9 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) 
     // (M + h D) a' = qfrc_smooth + qfrc_constraint  ( = M a - gradient at the solver's exit point)
     float *M = SF(M), *H = SF(H);
     const int t0 = CI(dof_t0)[lane], t1 = CI(dof_t1)[lane];
-    MJB_NOUNROLL
-    for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) H[i] = M[i];
-    MJB_SYNC();
-    if (lane < nv) H[tri(lane, lane)] += h * CF(dof_damping)[lane];
-    MJB_SYNC();
     float rhs = lane < nv ? SF(vecA)[lane] - SF(vecB)[lane] : 0.f;
-    float invd = cholesky(H, lane, t0, t1, dm.maxtree);
-    acc = chol_solve(H, lane, t0, t1, dm.maxtree, invd, rhs);
+    MJB_SYNC();
+    acc = factor_solve(M, H, lane, t0, t1, dm.maxtree, lane < nv ? h * CF(dof_damping)[lane] : 0.f, rhs, nv);
   }
   if (lane < nv) qvel[lane] += h * acc;
   MJB_SYNC();

@@ -66,6 +66,7 @@ struct Sim {
   int solver_iters = 100, ls_iters = 50;
   int last_solver_iters = 0;
   bool warmstart = true;
+  int warmstart_mode = 1;
   int contact_geom_out[2 * 256];
 };
 
@@ -591,7 +592,8 @@ void solve_newton(Sim& s, bool fixed_iters) {
   std::vector<double>& a = s.qacc;
   // warm start: whichever of qacc_warmstart / qacc_smooth has the lower cost
   a = s.qacc_smooth;
-  if (s.warmstart) {
+  if (s.warmstart_mode == 2) a = s.qacc_warmstart;  // always (what the CUDA path does)
+  else if (s.warmstart) {
     if (primal_cost(s, s.qacc_warmstart) < primal_cost(s, s.qacc_smooth)) a = s.qacc_warmstart;
   }
   std::vector<double> jar(ne), jv(ne), grad(nv), sv(nv), H((size_t)nv * nv), Mv(nv), Ma(nv);
@@ -997,7 +999,7 @@ void orc_destroy(void* p) {
 }
 void orc_set_solver(void* p, int mode, int iters, int warmstart) {
   Sim* s = (Sim*)p;
-  s->solver_mode = mode; s->solver_iters = iters; s->warmstart = warmstart != 0;
+  s->solver_mode = mode; s->solver_iters = iters; s->warmstart = warmstart != 0; s->warmstart_mode = warmstart;
 }
 void orc_reset(void* p) {
   Sim* s = (Sim*)p;

@@ -105,7 +105,7 @@ class OracleSim:
     solver_iters = property(lambda s: s._lib.orc_solver_iters(s._h))
 
     def set_solver(self, mode=0, iters=100, warmstart=True):
-        self._lib.orc_set_solver(self._h, mode, iters, 1 if warmstart else 0)
+        self._lib.orc_set_solver(self._h, mode, iters, int(warmstart))
 
     def reset(self):
         self._lib.orc_reset(self._h)
