@@ -380,7 +380,9 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   sizes[SF_M] = tri; sizes[SF_H] = tri;
   sizes[SF_cand] = dm.maxcand;
   sizes[SF_con] = CON_STRIDE * dm.maxcon;
-  sizes[SF_J] = 3 * dm.maxcon * dm.ldj;
+  sizes[SF_J] = std::max(3 * dm.maxcon * dm.ldj, MJB_MAX_AGENTS * (MJB_STORE_I_COUNT + MJB_STORE_F_COUNT) + 64 + 4);
+  if (spec.n_agents * MJB_STORE_I_COUNT > 64 || spec.n_agents * r4(std::max(1, spec.act_dim)) > 64 || spec.n_agents * MJB_STORE_F_COUNT > 32)
+    throw std::runtime_error("kernel limit: per-env plugin rows exceed the epilogue staging area");
   sizes[SF_efcD] = sizes[SF_efcAref] = sizes[SF_efcJar] = sizes[SF_efcJv] = dm.maxefc;
   sizes[SF_vecA] = sizes[SF_vecB] = sizes[SF_vecC] = sizes[SF_vecD] = nv;
   sizes[SF_rk] = m.integrator == MJB_INT_RK4 ? (m.nq + 3 * nv) : 1;

@@ -25,12 +25,10 @@ MJB_DEV float probe_dist(const float* probe, int a, int b) {
 
 // the dynamics / reward / done programme of one env, executed by one lane in the reference's order
 // (dynamic outer, agent inner; then reward fn outer, agent inner; truncation; done fns with early exit)
-MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_reset, const float* probe) {
+MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_reset, const float* probe, int* si, float* sf,
+                         const float* act, int* ts_io) {
   const DevModel& dm = *c.dm;
   const int A = dm.n_agents;
-  int* si = B.store_i + (size_t)env * A * dm.store_i32;
-  float* sf = B.store_f + (size_t)env * A * dm.store_f32;
-  const float* act = B.actions + (size_t)env * A * dm.act_stride;
   float* obs = B.obs + (size_t)env * A * dm.obs_stride;
   float* rew = B.reward + (size_t)env * A;
   uint8_t* term = B.term + (size_t)env * (A + 1);
@@ -99,7 +97,7 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
       rew[a] = 0.f; term[a] = 0; trunc[a] = 0;
     }
     term[A] = 0; trunc[A] = 0;
-    B.timestep[env] = 0;
+    *ts_io = 0;
     return;
   }
   MJB_NOUNROLL
@@ -136,7 +134,7 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
       }
     }
   }
-  int ts = B.timestep[env];
+  int ts = *ts_io;
   uint8_t tr = ts >= dm.max_steps ? 1 : 0;
   MJB_NOUNROLL
   for (int a = 0; a <= A; a++) trunc[a] = tr;
@@ -153,7 +151,7 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
   MJB_NOUNROLL
   for (int a = 0; a < A; a++) { rew[a] = reward[a]; term[a] = done[a] ? 1 : 0; }
   term[A] = all ? 1 : 0;
-  B.timestep[env] = ts + 1;
+  *ts_io = ts + 1;
 }
 
 // whole per-env pipeline.  Every lane of the warp calls this with the same arguments.
@@ -185,6 +183,25 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
     for (int i = lane; i < dm.nu; i += 32) ctrl[i] = g_ctrl[i];
   }
   MJB_NOUNROLL
+  // the plugin store, this env's step counter and the dynamic actions are fetched now so that their
+  // global-memory latency hides behind the physics; they are consumed by the epilogue
+  const int A_ = dm.n_agents;
+  const bool epi = (mode == MODE_STEP || mode == MODE_RESET);
+  int pre_si[2] = {0, 0};
+  float pre_sf = 0.f, pre_act[2] = {0.f, 0.f};
+  int pre_ts = 0;
+  if (epi) {
+    const int* gsi = B.store_i + (size_t)env * A_ * dm.store_i32;
+    const float* gsf = B.store_f + (size_t)env * A_ * dm.store_f32;
+    const float* gact = B.actions + (size_t)env * A_ * dm.act_stride;
+    for (int r = 0; r < 2; r++) {
+      int i = lane + 32 * r;
+      if (i < A_ * dm.store_i32) pre_si[r] = gsi[i];
+      if (i < A_ * dm.act_stride) pre_act[r] = gact[i];
+    }
+    if (lane < A_ * dm.store_f32) pre_sf = gsf[lane];
+    if (lane == 0) pre_ts = B.timestep[env];
+  }
   for (int i = lane; i < dm.nsensordata; i += 32) sens[i] = mode == MODE_RESET ? 0.f : g_sens[i];
   MJB_NOUNROLL
   for (int i = lane; i < 4 * dm.nprobe; i += 32) probe[i] = g_probe[i];
@@ -250,8 +267,26 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
       oa[i] = kind == 0 ? sens[adr] : (kind == 1 ? qpos[adr] : qvel[adr]);
     }
   }
+  // stage the prefetched rows in shared memory (the contact Jacobian scratch is dead by now)
+  int* s_si = (int*)SF(J);
+  float* s_sf = SF(J) + MJB_MAX_AGENTS * MJB_STORE_I_COUNT;
+  float* s_act = s_sf + MJB_MAX_AGENTS * MJB_STORE_F_COUNT;
+  int* s_ts = (int*)(s_act + 64);
+  for (int r = 0; r < 2; r++) {
+    int i = lane + 32 * r;
+    if (i < A_ * dm.store_i32) s_si[i] = pre_si[r];
+    if (i < A_ * dm.act_stride) s_act[i] = pre_act[r];
+  }
+  if (lane < A_ * dm.store_f32) s_sf[lane] = pre_sf;
+  if (lane == 0) *s_ts = pre_ts;
   MJB_SYNC();
-  if (lane == 0) run_plugins(c, B, env, mode == MODE_RESET, probe);
+  if (lane == 0) run_plugins(c, B, env, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
+  MJB_SYNC();
+  int* gsi = B.store_i + (size_t)env * A_ * dm.store_i32;
+  float* gsf = B.store_f + (size_t)env * A_ * dm.store_f32;
+  for (int i = lane; i < A_ * dm.store_i32; i += 32) gsi[i] = s_si[i];
+  if (lane < A_ * dm.store_f32) gsf[lane] = s_sf[lane];
+  if (lane == 0) B.timestep[env] = *s_ts;
 }
 
 }  // namespace mjb
