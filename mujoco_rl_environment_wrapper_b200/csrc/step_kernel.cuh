@@ -1169,11 +1169,12 @@ MJB_DEV void sensors_acc(const Ctx& c, int ncon) {
 
 // =================================================================================================
 // one forward-dynamics evaluation: SF_qpos / qvel / ctrl -> SF_qacc.  Returns the contact count.
-MJB_DEV int forward(const Ctx& c, bool sensors, int* iters_out) {
+MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out) {
   fk(c);
-  if (sensors) {
-    // exported positions belong to THIS forward pass, i.e. to the state before the integration that
-    // follows; taken now because xipos is recycled by the solver scratch below
+  if (probes) {
+    // exported positions belong to the LAST forward pass of the step (what `data.xipos` holds after
+    // mj_step): for Euler that is the state before the integration, for RK4 the fourth stage.
+    // Taken now because xipos is recycled by the solver scratch below
     const DevModel& dm = *c.dm;
     MJB_NOUNROLL
     for (int p = c.lane; p < dm.nprobe; p += 32) {
@@ -1244,7 +1245,7 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) 
       if (lane < nv) qvel[lane] = v0[lane] + h * A * aprev;
       MJB_SYNC();
     }
-    ncon = forward(c, sensors && st == 0, st == 0 ? iters_out : nullptr);
+    ncon = forward(c, sensors && st == 0, sensors && st == nstage - 1, st == 0 ? iters_out : nullptr);
     if (rk4) {
       const float Bw = (st == 0 || st == 3) ? (1.f / 6) : (1.f / 3);
       if (st == 0) {

@@ -202,3 +202,110 @@ def test_no_cpu_fallback_symbols_loaded():
     n0 = b.launch_count
     b.reset(); b.physics(2); b.forward(); b.sync()
     assert b.launch_count == n0 + 3
+
+
+def _mirror_env(env, e, seed, dynamics, rewards, dones, targets, **kw):
+    lib = L.load()
+    return H.OracleEnv(env.model, env._tables, env.agents, dynamics=dynamics, reward_functions=rewards, done_functions=dones,
+                       targets=targets, draw=(lambda a, k: lib.mjb_draw_u32(seed, e, a, k)), resolve=_resolver(env.model), **kw)
+
+
+def _sync_state(env, mirrors):
+    b, m = env.batch, env.model
+    b.qpos[:, :m.nq] = torch.tensor(np.stack([x.sim.qpos for x in mirrors]), dtype=torch.float32)
+    b.qvel[:, :m.nv] = torch.tensor(np.stack([x.sim.qvel for x in mirrors]), dtype=torch.float32)
+    if m.nu:
+        b.ctrl[:, :m.nu] = torch.tensor(np.stack([x.sim.ctrl for x in mirrors]), dtype=torch.float32)
+
+
+def test_pick_up_dynamic_C5():
+    """Config C5: Pick_Up dynamic re-expressed per agent (Testing/Pick_Up_Dynamic.py): inventory toggles,
+    target re-draws and the 4 appended observations, against the reference-order host loop on identical draws."""
+    import os
+    from common import LEVELS
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    from mujoco_rl_environment_wrapper_b200 import plugins as P
+    N, seed = 32, 77
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
+                    "agents": ["sender", "receiver"], "num_envs": N, "seed": seed, "environmentDynamics": [P.PickUpDynamic]})
+    assert env.observation_space("sender").shape == (63,) and env.action_space("sender").shape == (8,)
+    mirrors = [_mirror_env(env, e, seed, [H.PickUp], [], [], ["choice_1", "choice_2"]) for e in range(N)]
+    env.reset()
+    for m in mirrors:
+        m.reset({a: np.zeros(8) for a in env.agents})
+    rng = np.random.default_rng(9)
+    toggles = 0
+    for t in range(8):
+        for e, m in enumerate(mirrors):
+            if t in (2, 5) and e % 2 == 0:           # drop the sender next to a target (distance < 2 -> pick up)
+                m.sim.qpos[0:3] = [6.0, -1.5, 1.3] if (e // 2) % 2 == 0 else [1.0, -1.2, 1.3]
+        _sync_state(env, mirrors)
+        act = rng.uniform(-1, 1, (N, 2, 8)).astype(np.float32)
+        o, r, term, trunc, info = env.step({a: torch.tensor(act[:, i]) for i, a in enumerate(env.agents)})
+        for e, m in enumerate(mirrors):
+            mo, mr, mterm, mtrunc, _ = m.step({a: act[e, i] for i, a in enumerate(env.agents)})
+            for i, a in enumerate(env.agents):
+                g = o[a][e].cpu().numpy()
+                assert rel_err(g[:59], mo[a][:59]) < RTOL
+                assert np.allclose(g[59:62], mo[a][59:62], atol=1e-5)          # target position
+                assert g[62] == mo[a][62]                                        # inventory, exact
+                assert r[a][e].item() == mr[a]                                   # 0 / 1, exact
+                toggles += int(mr[a])
+    assert toggles > 0
+    assert set(info["sender"].keys()) == {"PickUpDynamic"}
+
+
+def test_ant_reward_rk4_C3_and_skipframes():
+    """Config C3 physics-on: Ant.xml (RK4, dt 0.01), ant_reward_function, skipFrames = 5 (ant_learning_perf.py:51-53)."""
+    import os
+    from common import LEVELS
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    from mujoco_rl_environment_wrapper_b200 import plugins as P
+    N = 16
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "Ant.xml"), "agents": ["torso"], "num_envs": N, "skipFrames": 5,
+                    "rewardFunctions": [P.ant_reward_function], "maxSteps": 3})
+    mirrors = [_mirror_env(env, e, 0, [], [H.ant_reward], [], [], skip_frames=5, max_steps=3) for e in range(N)]
+    env.reset()
+    for m in mirrors:
+        m.reset({"torso": np.zeros(8)})
+    rng = np.random.default_rng(4)
+    for t in range(6):
+        _sync_state(env, mirrors)
+        act = rng.uniform(-1, 1, (N, 1, 8)).astype(np.float32)
+        o, r, term, trunc, info = env.step({"torso": torch.tensor(act[:, 0])})
+        for e, m in enumerate(mirrors):
+            mo, mr, mterm, mtrunc, _ = m.step({"torso": act[e, 0]})
+            assert rel_err(o["torso"][e].cpu().numpy(), mo["torso"]) < 5 * RTOL      # 5 RK4 substeps
+            assert abs(r["torso"][e].item() - mr["torso"]) < 2e-2 * max(1.0, abs(mr["torso"]))  # (dx / dt) amplifies fp32 by 100
+            assert bool(trunc["torso"][e]) == mtrunc["torso"] and bool(trunc["__all__"][e]) == mtrunc["__all__"]
+        assert "__all__" not in term                # no done function configured (SURVEY 3.3)
+
+
+def test_sensor_scene_C4_skipframes5_freejoint():
+    """Config C4: 3-sensor level, freeJoint actions, skipFrames = 5 (sensor_test.py:18-20)."""
+    model, tables, agents, fj = load_scene("3S")
+    spec, keep = make_spec(model, tables, agents, fj, skip_frames=5)
+    N = 24
+    b = _batch(model, spec, N, keep)
+    b.reset(); b.sync()
+    sims = [OracleSim(model.blob) for _ in range(N)]
+    for s in sims:
+        s.forward()
+    rng = np.random.default_rng(8)
+    idx = tables.agents_action_index["sender"] + tables.agents_action_index["receiver"]
+    for t in range(30):
+        act = rng.uniform(-1, 1, (N, 2, 3)).astype(np.float32)
+        b.qpos[:, :30] = torch.tensor(np.stack([s.qpos for s in sims]), dtype=torch.float32)
+        b.qvel[:, :28] = torch.tensor(np.stack([s.qvel for s in sims]), dtype=torch.float32)
+        b.actions[:, :, :3] = torch.tensor(act)
+        b.step(); b.sync()
+        obs = b.obs.cpu().numpy()
+        for e, s in enumerate(sims):
+            s.qvel[idx] = act[e].reshape(-1)
+            for _ in range(5):
+                s.step()
+            for i, a in enumerate(agents):
+                oi = tables.agents_observation_index[a]
+                ref = np.concatenate([s.sensordata[oi["sensors"]], s.qpos, s.qvel])
+                assert rel_err(obs[e, i, :63][5:], ref[5:]) < 5 * RTOL, (t, e)
+                assert rel_err(obs[e, i, :5], ref[:5]) < 5e-3, (t, e, obs[e, i, :5], ref[:5])
