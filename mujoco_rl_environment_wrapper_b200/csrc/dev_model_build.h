@@ -85,7 +85,7 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   dm.nsite = m.nsite; dm.nsensor = m.nsensor; dm.nsensordata = m.nsensordata; dm.npair = m.npair;
   dm.nlevel = nlevel; dm.integrator = m.integrator; dm.timestep = (float)m.timestep;
   for (int i = 0; i < 3; i++) dm.gravity[i] = (float)m.gravity[i];
-  dm.ldm = m.nv | 1; dm.ldj = m.nv | 1;
+  dm.ldm = m.nv | 1; dm.ldj = m.nv | 1;  // ldj is narrowed below to the widest contact dof mask
   dm.solver_iterations = spec.solver_iterations > 0 ? spec.solver_iterations : env_int("MJB_SOLVER_ITERS", 24);
   dm.ls_iterations = spec.ls_iterations > 0 ? spec.ls_iterations : env_int("MJB_LS_ITERS", 12);
   {
@@ -362,6 +362,21 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   while (W.size() % 4) W.push_back(0);
   dm.image_words = (int)W.size();
 
+  // packed contact Jacobian width: the widest chain(b1) xor chain(b2) over the collision pair table
+  {
+    auto chain = [&](int body) {
+      uint64_t mask = 0;
+      for (int b = body; b > 0; b = m.body_parentid[b])
+        for (int d = m.body_dofadr[b]; d >= 0 && d < m.body_dofadr[b] + m.body_dofnum[b]; d++) mask |= (1ull << d);
+      return mask;
+    };
+    int widest = 1;
+    for (int k = 0; k < m.npair; k++) {
+      uint64_t x = chain(m.geom_bodyid[m.pair_geom1[k]]) ^ chain(m.geom_bodyid[m.pair_geom2[k]]);
+      widest = std::max(widest, (int)__builtin_popcountll(x));
+    }
+    dm.ldj = widest | 1;  // odd stride: lane = row accesses stay bank-conflict free
+  }
   // ---- limits on per-env scratch
   int dflt_con = ngdyn >= 16 ? 12 : 8;
   dm.maxcon = std::max(1, env_int("MJB_MAXCON", dflt_con));
@@ -392,6 +407,13 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   const bool alias_H = tri <= r4(sizes[SF_cinert]) + r4(sizes[SF_crb]);
   if (dm.maxcand > r4(sizes[SF_cvel]) + r4(sizes[SF_cacc])) dm.maxcand = std::max(32, r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]) - 4);
   const bool alias_cand = dm.maxcand <= r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]);
+  // without acceleration-stage sensors nothing touches cvel / cacc after the bias pass: the contact
+  // records can live there too (behind the candidate list)
+  bool alias_con = false;
+  if (alias_cand && !dm.need_acc_sensors) {
+    int room = r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]) - r4(sizes[SF_con]);
+    if (room >= 64) { alias_con = true; dm.maxcand = std::min(dm.maxcand, room & ~3); }
+  }
   sizes[SF_cand] = dm.maxcand;
   // the per-row constraint vectors and the nv-sized solver temporaries live where xquat + xmat + xipos
   // were: those are dead once the kinematics pass has produced geom frames, inertias and probes
@@ -407,6 +429,7 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   for (int i = 0; i < SF_COUNT; i++) {
     if (i == SF_H && alias_H) { dm.soff[i] = dm.soff[SF_cinert]; continue; }
     if (i == SF_cand && alias_cand) { dm.soff[i] = dm.soff[SF_cvel]; continue; }
+    if (i == SF_con && alias_con) { dm.soff[i] = dm.soff[SF_cvel] + r4(dm.maxcand); continue; }
     if (aliased[i]) continue;  // placed below
     dm.soff[i] = off; off += r4(sizes[i]);
   }

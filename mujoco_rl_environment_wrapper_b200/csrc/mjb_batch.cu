@@ -44,7 +44,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // One CTA per SM slot, `warps` environments in flight per CTA; each warp walks the env index space
 // with a grid-wide stride (envs are independent, no inter-warp communication after the staging).
 __global__ void k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
-                      int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env) {
+                      int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env,
+                      int lockstep) {
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* img = smem + 4;  // 16 B after the barrier
@@ -66,6 +67,17 @@ __global__ void k_env(const __grid_constant__ DevModel dm, const uint32_t* __res
   // dynamic env scheduling: per-env cost varies (contact count, Newton iterations), so every warp pulls
   // its next env from a grid-wide counter instead of owning a fixed slice
   int env = blockIdx.x * warps + warp;
+  if (lockstep) {
+    // CTA-wide rounds: all env-warps of the SM re-align at every env boundary, so they walk through the
+    // (large) step code together and share instruction-cache lines; costs waiting for the slowest env.
+    const int stride = gridDim.x * warps;
+    const int rounds = (num_envs - blockIdx.x * warps + stride - 1) / stride;
+    for (int r = 0; r < rounds; r++, env += stride) {
+      if (env < num_envs) run_env(c, B, env, mode, skip_frames, mask);
+      __syncthreads();
+    }
+    return;
+  }
   while (env < num_envs) {
     run_env(c, B, env, mode, skip_frames, mask);
     __syncwarp();
@@ -86,6 +98,7 @@ struct mjb_batch {
   uint32_t* d_image = nullptr;
   int* d_next = nullptr;   // ring of work counters, one per in-flight launch
   int next_slot = 0;
+  int lockstep = 0;
   int64_t launches = 0;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -119,7 +132,7 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
   CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, b->stream));
   (void)first;
   mjb::k_env<<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode,
-                                                                     skip_frames, mask, counter);
+                                                                     skip_frames, mask, counter, b->lockstep);
   CUDA_TRY(cudaGetLastError());
   if (b->timing) {
     CUDA_TRY(cudaEventRecord(e1, b->stream));
@@ -184,7 +197,7 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
   size_t fixed = 16 + (size_t)dm.image_words * 4;
   size_t per_env = ((size_t)dm.env_words + 4 * ((dm.nprobe + 3) & ~3)) * 4;
   int warps = (int)((max_smem - fixed) / per_env);
-  int cap = mjb::env_int("MJB_WARPS", 16);
+  int cap = mjb::env_int("MJB_WARPS", 18);
   if (warps > cap) warps = cap;
   if (warps < 1) { mjb::set_error("model needs more shared memory per environment than one SM has"); return fail(MJB_ERR_LIMIT); }
   // even out the rounds: the fewest warps per CTA that keeps the same number of passes over the envs
@@ -210,6 +223,7 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     return fail(MJB_ERR_CUDA);
   }
   b->h_first[0] = b->grid * b->warps;
+  b->lockstep = mjb::env_int("MJB_LOCKSTEP", 1);
   const int A = dm.n_agents;
   if (cudaMallocHost(&b->h_act, sizeof(float) * (size_t)num_envs * A * dm.act_stride + 16) != cudaSuccess ||
       cudaMallocHost(&b->h_obs, sizeof(float) * (size_t)num_envs * A * dm.obs_stride + 16) != cudaSuccess ||

@@ -653,30 +653,39 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
       efcD[2 * k + side] = D; efcAref[2 * k + side] = aref;
     }
   }
-  // contact Jacobians: lane = dof, rows (normal, tangent1, tangent2) per contact
+  // contact Jacobians: lane = dof, rows (normal, tangent1, tangent2) per contact.  Only the dofs on the
+  // chains of the two bodies are non-zero, so each row is stored PACKED along the set bits of the contact's
+  // dof mask (mask = chain(b1) xor chain(b2): shared ancestors cancel), ldj = widest mask + padding.
   float *J = SF(J), *con = SF(con), *cdof = SF(cdof), *xpos = SF(xpos);
   const uint32_t* pairs = CU(pair_pack);
+  MJB_NOUNROLL
+  for (int k = c.lane; k < ncon; k += 32) {
+    float* r = con + CON_STRIDE * k;
+    uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
+    int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
+    ((uint32_t*)r)[CON_MASK] = (b1 >= 0 ? CU(mb_dofmask)[2 * b1] : 0u) ^ (b2 >= 0 ? CU(mb_dofmask)[2 * b2] : 0u);
+  }
+  MJB_SYNC();
   MJB_NOUNROLL
   for (int d = c.lane; d < dm.nv; d += 32) {
     f3 sw = ld3(cdof + 6 * d), sv = ld3(cdof + 6 * d + 3);
     int root = CI(mb_root)[CI(dof_mb)[d]];
     f3 o = ld3(xpos + 3 * root);
-    uint32_t bit = 1u << (d & 31);
-    int word = d >> 5;
+    uint32_t bit = 1u << d;
     MJB_NOUNROLL
     for (int k = 0; k < ncon; k++) {
       const float* r = con + CON_STRIDE * k;
+      uint32_t mask = ((const uint32_t*)r)[CON_MASK];
+      if (!(mask & bit)) continue;
       uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
-      int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
-      int s = 0;
-      if (b2 >= 0 && (CU(mb_dofmask)[2 * b2 + word] & bit)) s += 1;
-      if (b1 >= 0 && (CU(mb_dofmask)[2 * b1 + word] & bit)) s -= 1;
-      float jn = 0.f, jt1 = 0.f, jt2 = 0.f;
-      if (s != 0) {
-        f3 vel = (sv + cross(sw, ld3(r + CON_POS) - o)) * (float)s;
-        jn = dot(ld3(r + CON_FRAME), vel); jt1 = dot(ld3(r + CON_FRAME + 3), vel); jt2 = dot(ld3(r + CON_FRAME + 6), vel);
-      }
-      J[(3 * k) * dm.ldj + d] = jn; J[(3 * k + 1) * dm.ldj + d] = jt1; J[(3 * k + 2) * dm.ldj + d] = jt2;
+      int b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
+      // the dof is on exactly one of the two chains: + for geom2's body, - for geom1's
+      float sgn = (b2 >= 0 && (CU(mb_dofmask)[2 * b2] & bit)) ? 1.f : -1.f;
+      f3 vel = (sv + cross(sw, ld3(r + CON_POS) - o)) * sgn;
+      int idx = MJB_POPC(mask & (bit - 1u));
+      J[(3 * k) * dm.ldj + idx] = dot(ld3(r + CON_FRAME), vel);
+      J[(3 * k + 1) * dm.ldj + idx] = dot(ld3(r + CON_FRAME + 3), vel);
+      J[(3 * k + 2) * dm.ldj + idx] = dot(ld3(r + CON_FRAME + 6), vel);
     }
   }
   MJB_SYNC();
@@ -692,10 +701,16 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
     float mu = pc[PC_MU], dist = r[CON_DIST], inc = pc[PC_INCMARGIN];
     float imp = impedance(pc + PC_SOLIMP, dist, inc);
     float vn = 0.f, v1 = 0.f, v2 = 0.f;
-    MJB_NOUNROLL
-    for (int d = 0; d < dm.nv; d++) {
-      float qd = qvel[d];
-      vn += J[(3 * k) * dm.ldj + d] * qd; v1 += J[(3 * k + 1) * dm.ldj + d] * qd; v2 += J[(3 * k + 2) * dm.ldj + d] * qd;
+    {
+      uint32_t mm = ((const uint32_t*)r)[CON_MASK];
+      int m = 0;
+      MJB_NOUNROLL
+      while (mm) {
+        float qd = qvel[MJB_FFS(mm) - 1];
+        mm &= mm - 1;
+        vn += J[(3 * k) * dm.ldj + m] * qd; v1 += J[(3 * k + 1) * dm.ldj + m] * qd; v2 += J[(3 * k + 2) * dm.ldj + m] * qd;
+        m++;
+      }
     }
     float kpos = pc[PC_K] * imp * (dist - inc), B = pc[PC_B];
     if (pc[PC_CONDIM] < 2.f) {
@@ -872,13 +887,15 @@ MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const 
   int base = 2 * dm.nlim;
   MJB_NOUNROLL
   for (int r = c.lane; r < 3 * ncon; r += 32) {
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f;
     const float* jr = J + r * dm.ldj;
-    int d = 0;
+    uint32_t mm = ((const uint32_t*)(con + CON_STRIDE * (r / 3)))[CON_MASK];
     MJB_NOUNROLL
-    for (; d + 1 < dm.nv; d += 2) { s0 += jr[d] * x[d]; s1 += jr[d + 1] * x[d + 1]; }
-    if (d < dm.nv) s0 += jr[d] * x[d];
-    out[base + 4 * (r / 3) + (r % 3)] = s0 + s1;
+    while (mm) {
+      s0 += *jr++ * x[MJB_FFS(mm) - 1];
+      mm &= mm - 1;
+    }
+    out[base + 4 * (r / 3) + (r % 3)] = s0;
   }
   MJB_SYNC();
   MJB_NOUNROLL
@@ -928,8 +945,12 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
         float f1 = jar[base + 4 * k + 1] < 0 ? -D[base + 4 * k + 1] * jar[base + 4 * k + 1] : 0.f;
         float f2 = jar[base + 4 * k + 2] < 0 ? -D[base + 4 * k + 2] * jar[base + 4 * k + 2] : 0.f;
         float f3_ = jar[base + 4 * k + 3] < 0 ? -D[base + 4 * k + 3] * jar[base + 4 * k + 3] : 0.f;
-        g -= J[(3 * k) * dm.ldj + lane] * (f0 + f1 + f2 + f3_) + J[(3 * k + 1) * dm.ldj + lane] * mu * (f0 - f1) +
-             J[(3 * k + 2) * dm.ldj + lane] * mu * (f2 - f3_);
+        uint32_t mask = ((const uint32_t*)(con + CON_STRIDE * k))[CON_MASK];
+        if ((mask >> lane) & 1u) {
+          int idx = MJB_POPC(mask & ((1u << lane) - 1u));
+          g -= J[(3 * k) * dm.ldj + idx] * (f0 + f1 + f2 + f3_) + J[(3 * k + 1) * dm.ldj + idx] * mu * (f0 - f1) +
+               J[(3 * k + 2) * dm.ldj + idx] * mu * (f2 - f3_);
+        }
       }
       grad[lane] = g;
     }
@@ -959,7 +980,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     for (int k = 0; k < ncon; k++) {
       uint32_t pk = pairs[((const int*)(con + CON_STRIDE * k))[CON_PAIR]];
       int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
-      uint32_t mask = (b1 >= 0 ? CU(mb_dofmask)[2 * b1] : 0u) ^ (b2 >= 0 ? CU(mb_dofmask)[2 * b2] : 0u);
+      uint32_t mask = ((const uint32_t*)(con + CON_STRIDE * k))[CON_MASK];
       float mu = con[CON_STRIDE * k + CON_MU];
       float w0 = jar[base + 4 * k] < 0 ? D[base + 4 * k] : 0.f, w1 = jar[base + 4 * k + 1] < 0 ? D[base + 4 * k + 1] : 0.f;
       float w2 = jar[base + 4 * k + 2] < 0 ? D[base + 4 * k + 2] : 0.f, w3 = jar[base + 4 * k + 3] < 0 ? D[base + 4 * k + 3] : 0.f;
@@ -969,16 +990,21 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       float cn1 = mu * (w0 - w1), c11 = mu * mu * (w0 + w1), cn2 = mu * (w2 - w3), c22 = mu * mu * (w2 + w3);
       bool mine = lane < nv && ((mask >> lane) & 1u);
       float jn = 0.f, j1 = 0.f, j2 = 0.f;
-      if (mine) { jn = J[(3 * k) * dm.ldj + lane]; j1 = J[(3 * k + 1) * dm.ldj + lane]; j2 = J[(3 * k + 2) * dm.ldj + lane]; }
+      if (mine) {
+        int idx = MJB_POPC(mask & ((1u << lane) - 1u));
+        jn = J[(3 * k) * dm.ldj + idx]; j1 = J[(3 * k + 1) * dm.ldj + idx]; j2 = J[(3 * k + 2) * dm.ldj + idx];
+      }
       // row i (lane) x column j (set bits of mask, j <= i)
       float ri_n = cnn * jn + cn1 * j1 + cn2 * j2, ri_1 = cn1 * jn + c11 * j1, ri_2 = cn2 * jn + c22 * j2;
       uint32_t mm = mask;
+      int m = 0;
       MJB_NOUNROLL
       while (mm) {
         int j = MJB_FFS(mm) - 1;
         mm &= mm - 1;
         if (mine && j <= lane)
-          H[tri(lane, j)] += ri_n * J[(3 * k) * dm.ldj + j] + ri_1 * J[(3 * k + 1) * dm.ldj + j] + ri_2 * J[(3 * k + 2) * dm.ldj + j];
+          H[tri(lane, j)] += ri_n * J[(3 * k) * dm.ldj + m] + ri_1 * J[(3 * k + 1) * dm.ldj + m] + ri_2 * J[(3 * k + 2) * dm.ldj + m];
+        m++;
       }
     }
     MJB_SYNC();
