@@ -175,6 +175,10 @@ int64_t mjb_launch_count(const mjb_batch* b);
  * recorded around each launch when enabled with mjb_set_timing(b, 1) */
 int mjb_set_timing(mjb_batch* b, int32_t enable);
 int mjb_kernel_time_ms(mjb_batch* b, double* total_ms, int64_t* launches);
+/* Optional scheduling hint: a device permutation of [0, num_envs) (NULL = identity).  Consecutive entries
+ * share an SM round, so ordering envs by their last solver cost (buffers.niter) evens the rounds out.
+ * Results do not depend on it (envs are independent). */
+int mjb_set_env_order(mjb_batch* b, const int32_t* order_dev);
 /* launch geometry chosen at creation: CTAs, env-warps per CTA, dynamic shared memory per CTA */
 int mjb_batch_geometry(const mjb_batch* b, int32_t* grid, int32_t* warps_per_cta, int64_t* smem_bytes);
 /* counter-based draw used for target selection: exported so tests can reproduce the stream */

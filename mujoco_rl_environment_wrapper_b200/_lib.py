@@ -107,6 +107,7 @@ def load(build_if_missing=True):
     lib.mjb_launch_count.argtypes = [vp]
     lib.mjb_set_timing.argtypes = [vp, i32]
     lib.mjb_kernel_time_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+    lib.mjb_set_env_order.argtypes = [vp, vp]
     lib.mjb_batch_geometry.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)]
     lib.mjb_draw_u32.restype = ctypes.c_uint32
     lib.mjb_draw_u32.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]

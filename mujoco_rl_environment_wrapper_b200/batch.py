@@ -5,6 +5,7 @@ CUDA tensors owned here (row-major, env-major, rows 16 B aligned); the library o
 pointers.  There is no CPU fallback: constructing a Batch without a CUDA device raises.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -48,6 +49,7 @@ class Batch:
                                                ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(B), ctypes.byref(h)),
                     "batch create")
         self._h = h
+        self.balance_every = int(os.environ.get("MJB_BALANCE_EVERY", "0"))
 
     def __del__(self):
         try:
@@ -73,6 +75,16 @@ class Batch:
 
     def step(self):
         L.check(self._lib.mjb_step(self._h), "step")
+        self._steps = getattr(self, "_steps", 0) + 1
+        if self.balance_every and self._steps % self.balance_every == 0:
+            self.rebalance()
+
+    def rebalance(self):
+        """Scheduling hint only: order envs by their last solver cost (Newton iterations, contacts) so that the
+        lock-step rounds of an SM hold envs of similar cost.  One device sort, no host sync."""
+        key = self.buf["niter"] * 64 + self.buf["ncon"]
+        self._order = torch.argsort(key).to(torch.int32)
+        L.check(self._lib.mjb_set_env_order(self._h, ctypes.c_void_p(self._order.data_ptr())), "env order")
 
     def physics(self, skip_frames=1):
         L.check(self._lib.mjb_physics(self._h, skip_frames), "physics")

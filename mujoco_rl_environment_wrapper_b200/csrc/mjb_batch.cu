@@ -43,9 +43,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // One CTA per SM slot, `warps` environments in flight per CTA; each warp walks the env index space
 // with a grid-wide stride (envs are independent, no inter-warp communication after the staging).
-__global__ void k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
+__global__ void __launch_bounds__(512, 1) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
                       int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env,
-                      int lockstep) {
+                      int lockstep, const int* __restrict__ env_order) {
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* img = smem + 4;  // 16 B after the barrier
@@ -63,27 +63,34 @@ __global__ void k_env(const __grid_constant__ DevModel dm, const uint32_t* __res
   mbar_wait(bar, 0);
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
-  Ctx c{&dm, img, scratch, lane, probe};
+  Ctx c{&dm, img, scratch, lane, probe, 0};
   // dynamic env scheduling: per-env cost varies (contact count, Newton iterations), so every warp pulls
   // its next env from a grid-wide counter instead of owning a fixed slice
+  // Two scheduling modes share ONE call site of the step code:
+  //  * lock-step rounds (default): every env-warp of the CTA takes one env per round and the CTA re-aligns
+  //    at each round boundary, so the warps walk through the (large) step code together and share
+  //    instruction-cache lines (measured 2x at 65536 envs); costs waiting for the slowest env of the round;
+  //  * dynamic: each warp pulls its next env from a grid-wide counter (better balance, poor i-cache reuse).
+  const int stride = gridDim.x * warps;
+  const int rounds = (num_envs - blockIdx.x * warps + stride - 1) / stride;
   int env = blockIdx.x * warps + warp;
-  if (lockstep) {
-    // CTA-wide rounds: all env-warps of the SM re-align at every env boundary, so they walk through the
-    // (large) step code together and share instruction-cache lines; costs waiting for the slowest env.
-    const int stride = gridDim.x * warps;
-    const int rounds = (num_envs - blockIdx.x * warps + stride - 1) / stride;
-    for (int r = 0; r < rounds; r++, env += stride) {
-      if (env < num_envs) run_env(c, B, env, mode, skip_frames, mask);
-      __syncthreads();
+  for (int r = 0;; r++) {
+    if (lockstep ? (r >= rounds) : (env >= num_envs)) break;
+    if (lockstep == 1) {
+      int busy = num_envs - (blockIdx.x * warps + r * stride);  // env-warps of this CTA with work in this round
+      // (a masked reset lets warps skip their env, so intra-step alignment is off for it)
+      c.cta_threads = (mask == nullptr ? 32 : 0) * (busy > warps ? warps : (busy < 0 ? 0 : busy));
     }
-    return;
-  }
-  while (env < num_envs) {
-    run_env(c, B, env, mode, skip_frames, mask);
-    __syncwarp();
-    int nxt = 0;
-    if (lane == 0) nxt = atomicAdd(next_env, 1);
-    env = __shfl_sync(0xffffffffu, nxt, 0);
+    if (env < num_envs) run_env(c, B, (lockstep && env_order) ? env_order[env] : env, mode, skip_frames, mask);
+    if (lockstep) {
+      __syncthreads();
+      env += stride;
+    } else {
+      __syncwarp();
+      int nxt = 0;
+      if (lane == 0) nxt = atomicAdd(next_env, 1);
+      env = __shfl_sync(0xffffffffu, nxt, 0);
+    }
   }
 }
 
@@ -99,6 +106,7 @@ struct mjb_batch {
   int* d_next = nullptr;   // ring of work counters, one per in-flight launch
   int next_slot = 0;
   int lockstep = 0;
+  const int* env_order = nullptr;
   int64_t launches = 0;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -132,7 +140,7 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
   CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, b->stream));
   (void)first;
   mjb::k_env<<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode,
-                                                                     skip_frames, mask, counter, b->lockstep);
+                                                                     skip_frames, mask, counter, b->lockstep, b->lockstep ? b->env_order : nullptr);
   CUDA_TRY(cudaGetLastError());
   if (b->timing) {
     CUDA_TRY(cudaEventRecord(e1, b->stream));
@@ -196,12 +204,16 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
   size_t max_smem = prop.sharedMemPerBlockOptin;
   size_t fixed = 16 + (size_t)dm.image_words * 4;
   size_t per_env = ((size_t)dm.env_words + 4 * ((dm.nprobe + 3) & ~3)) * 4;
-  int warps = (int)((max_smem - fixed) / per_env);
-  int cap = mjb::env_int("MJB_WARPS", 18);
+  // `ctas` lock-step groups per SM (each with its own copy of the model image and its own round barrier)
+  int ctas = std::max(1, mjb::env_int("MJB_CTAS_PER_SM", 1));
+  size_t sm_smem = prop.sharedMemPerMultiprocessor;
+  size_t cta_budget = std::min(max_smem, sm_smem / ctas - 1024);
+  int warps = cta_budget > fixed ? (int)((cta_budget - fixed) / per_env) : 0;
+  int cap = mjb::env_int("MJB_WARPS", 16);
   if (warps > cap) warps = cap;
   if (warps < 1) { mjb::set_error("model needs more shared memory per environment than one SM has"); return fail(MJB_ERR_LIMIT); }
   // even out the rounds: the fewest warps per CTA that keeps the same number of passes over the envs
-  int sms = prop.multiProcessorCount;
+  int sms = prop.multiProcessorCount * ctas;
   int rounds = (num_envs + sms * warps - 1) / (sms * warps);
   int even = (num_envs + sms * rounds - 1) / (sms * rounds);
   if (even < warps) warps = even < 1 ? 1 : even;
@@ -223,7 +235,7 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     return fail(MJB_ERR_CUDA);
   }
   b->h_first[0] = b->grid * b->warps;
-  b->lockstep = mjb::env_int("MJB_LOCKSTEP", 1);
+  b->lockstep = mjb::env_int("MJB_LOCKSTEP", 2);
   const int A = dm.n_agents;
   if (cudaMallocHost(&b->h_act, sizeof(float) * (size_t)num_envs * A * dm.act_stride + 16) != cudaSuccess ||
       cudaMallocHost(&b->h_obs, sizeof(float) * (size_t)num_envs * A * dm.obs_stride + 16) != cudaSuccess ||
@@ -315,6 +327,12 @@ int mjb_kernel_time_ms(mjb_batch* b, double* total_ms, int64_t* launches) {
   }
   *total_ms = tot; *launches = (int64_t)b->events.size();
   b->events.clear();
+  return MJB_OK;
+}
+
+int mjb_set_env_order(mjb_batch* b, const int32_t* order_dev) {
+  if (!b) { mjb::set_error("mjb_set_env_order: null batch"); return MJB_ERR_ARG; }
+  b->env_order = order_dev;
   return MJB_OK;
 }
 

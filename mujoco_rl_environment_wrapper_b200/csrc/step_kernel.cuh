@@ -84,6 +84,7 @@ struct Ctx {
   float* s;             // this env's scratch (shared memory)
   int lane;
   float* probe;         // exported positions of this env (shared memory, 4 floats per probe)
+  int cta_threads;      // threads of the CTA busy in this lock-step round (0 / 32: no CTA-level alignment)
 };
 #define CI(f) ((const int*)(c.img + c.dm->off[IF_##f]))
 #define CU(f) ((const uint32_t*)(c.img + c.dm->off[IF_##f]))
@@ -802,62 +803,63 @@ MJB_DEV float chol_solve(const float* A, int lane, int t0, int t1, int nb, float
   return x;
 }
 
-// Register-resident variant for blocks of at most MJB_NB rows (every level of the reference: 14 dofs per
-// ant): lane i keeps row i of its block in registers, row j is broadcast with shuffles, no shared-memory
-// traffic and no barriers inside the factorisation.  Solves (A + diag) x = b for the lane's block where A is
-// a packed lower triangle in shared memory; L is written to `Lout` (packed) for the backward substitution.
+// Register-resident variant for blocks of at most NBT rows (every level of the reference: 14 dofs per ant,
+// 6 for a free body): lane i keeps row i of its block in registers, row j is broadcast with shuffles, no
+// shared-memory traffic and no barriers inside the factorisation.  Solves (A + diag) x = b for the lane's
+// block where A is a packed lower triangle in shared memory; L is written to `Lout` (packed) for the
+// transposed solve.  Lanes of a block smaller than NBT (and idle lanes) run the same instruction stream on
+// garbage that is never stored: columns past the block's size only ever touch the unused upper triangle.
 #define MJB_NB 16
-MJB_DEV_NOINLINE float factor_solve_reg(const float* A, float* Lout, int lane, int t0, int t1, int nb, float diag_add, float b) {
-  float a[MJB_NB];
+template <int NBT>
+MJB_DEV_NOINLINE float factor_solve_regT(const float* A, float* Lout, int lane, int t0, int t1, float diag_add, float b) {
+  float a[NBT];
   const bool own = lane < t1;
   const int li = lane - t0;
+  const int rowoff = own ? tri(lane, t0) : 0;
 #pragma unroll
-  for (int k = 0; k < MJB_NB; k++) {
-    a[k] = (own && k <= li && k < nb) ? A[tri(lane, t0 + k)] : 0.f;
-    if (k == li) a[k] += diag_add;
+  for (int k = 0; k < NBT; k++) {
+    float v = (own && k <= li) ? A[rowoff + k] : 0.f;
+    a[k] = (k == li) ? v + diag_add : v;
   }
   float invd = 1.f;
 #pragma unroll
-  for (int j = 0; j < MJB_NB; j++) {
-    if (j < nb) {
-      const int src = (t0 + j < t1) ? t0 + j : lane;
-      float s = a[j];
+  for (int j = 0; j < NBT; j++) {
+    const int src = t0 + j;
+    float s = a[j];
 #pragma unroll
-      for (int k = 0; k < j; k++) s -= a[k] * MJB_SHFL(a[k], src);
-      float sj = MJB_SHFL(s, src);
-      float inv = MJB_RSQRT(fmaxf(sj, 1e-20f));
-      if (li == j) { invd = inv; a[j] = sj * inv; }
-      else if (li > j) a[j] = s * inv;
-    }
+    for (int k = 0; k < j; k++) s -= a[k] * MJB_SHFL(a[k], src);
+    float sj = MJB_SHFL(s, src);
+    float inv = MJB_RSQRT(fmaxf(sj, 1e-20f));
+    a[j] = (li == j ? sj : s) * inv;
+    if (li == j) invd = inv;
   }
-  // keep L for the transposed solve
 #pragma unroll
-  for (int k = 0; k < MJB_NB; k++)
-    if (own && k <= li && k < nb) Lout[tri(lane, t0 + k)] = a[k];
-  // forward substitution from registers
+  for (int k = 0; k < NBT; k++)
+    if (own && k <= li) Lout[rowoff + k] = a[k];
   float x = b;
 #pragma unroll
-  for (int k = 0; k < MJB_NB; k++) {
-    if (k < nb) {
-      const int src = (t0 + k < t1) ? t0 + k : lane;
-      float yk = MJB_SHFL(x * invd, src);
-      if (li == k) x = yk;
-      else if (li > k && own) x -= a[k] * yk;
-    }
+  for (int k = 0; k < NBT; k++) {
+    float yk = MJB_SHFL(x * invd, t0 + k);
+    x = (li == k) ? yk : (li > k ? x - a[k] * yk : x);
   }
   MJB_SYNC();
-  // backward substitution: column k of L is row-contiguous in the packed store
-  MJB_NOUNROLL
-  for (int kk = nb - 1; kk >= 0; kk--) {
+  // transposed solve: column k of L is contiguous across lanes in the packed store
+  const int colbase = tri(t0, 0) + lane;  // &L(t0 + kk, lane) = colbase + kk * t0 + kk (kk + 1) / 2
+#pragma unroll
+  for (int kk = NBT - 1; kk >= 0; kk--) {
     const int k = t0 + kk;
-    const bool col = own && k < t1;
-    float xk = MJB_SHFL(x * invd, col ? k : lane);
-    if (col) {
+    float xk = MJB_SHFL(x * invd, k);
+    if (own && k < t1) {
       if (lane == k) x = xk;
-      else if (lane < k) x -= Lout[tri(k, lane)] * xk;
+      else if (lane < k) x -= Lout[colbase + kk * t0 + (kk * (kk + 1)) / 2] * xk;
     }
   }
   return x;
+}
+MJB_DEV float factor_solve_reg(const float* A, float* Lout, int lane, int t0, int t1, int nb, float diag_add, float b) {
+  if (nb <= 6) return factor_solve_regT<6>(A, Lout, lane, t0, t1, diag_add, b);
+  if (nb <= 14) return factor_solve_regT<14>(A, Lout, lane, t0, t1, diag_add, b);
+  return factor_solve_regT<MJB_NB>(A, Lout, lane, t0, t1, diag_add, b);
 }
 // (A + diag) x = b per block; picks the register path when the blocks are small enough
 MJB_DEV float factor_solve(const float* A, float* L, int lane, int t0, int t1, int nb, float diag_add, float b, int nv) {
@@ -931,11 +933,14 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
   }
   rows_mul(c, ncon, a, jar, aref);
   int it = 0;
-  bool stalled = false;
+  bool stalled = false, done = false;
   MJB_NOUNROLL
-  for (;; it++) {
-    // gradient = M a - qfrc_smooth - J' f
+  for (;;) {
+    // Iterations are aligned across the env-warps of the CTA (they then share instruction-cache lines); a
+    // warp whose env has converged idles at the barrier until every env of the round is done.
     float g = 0.f;
+    if (!done) {
+    // gradient = M a - qfrc_smooth - J' f
     if (lane < nv) {
       g = Ma[lane] - qfrc[lane];
       MJB_NOUNROLL
@@ -964,7 +969,11 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     g = lane < nv ? grad[lane] : 0.f;
     float gn = wsum(g * g);
     float fn = wsum(lane < nv ? qfrc[lane] * qfrc[lane] + Ma[lane] * Ma[lane] : 0.f);
-    if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) break;
+    if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) done = true;
+    }
+    if (!MJB_CTA_ANY(c.cta_threads, !done)) break;
+    if (done) continue;
+    it++;
     // Hessian H = M + J' diag(D active) J (packed lower triangle)
     MJB_NOUNROLL
     for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) H[i] = M[i];
@@ -1212,10 +1221,14 @@ MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out) {
   }
   crb_mass(c);
   rne_pass(c, false);
+  MJB_CTA_SYNC(c.cta_threads);  // re-align the env-warps of the CTA before the data-dependent phases
   int ncon = collide(c);
   if (sensors) sensors_pos(c);
+  MJB_CTA_SYNC(c.cta_threads);
   make_constraints(c, ncon);
+  MJB_CTA_SYNC(c.cta_threads);
   int it = newton(c, ncon);
+  MJB_CTA_SYNC(c.cta_threads);
   if (iters_out) *iters_out = it;
   if (sensors) sensors_acc(c, ncon);
   return ncon;

@@ -20,6 +20,8 @@
 #define MJB_POPC(x) __builtin_popcount(x)
 #define MJB_FFS(x) __builtin_ffs(x)
 #define MJB_RSQRT(x) (1.0f / sqrtf(x))
+#define MJB_CTA_SYNC(nthreads) ((void)0)
+#define MJB_CTA_ANY(nthreads, pred) (pred)
 #else
 #define MJB_DEV __device__ __forceinline__
 #define MJB_DEV_NOINLINE __device__ __noinline__
@@ -32,6 +34,28 @@
 #define MJB_POPC(x) __popc(x)
 #define MJB_FFS(x) __ffs(x)
 #define MJB_RSQRT(x) rsqrtf(x)
+// CTA-level alignment of the env-warps that are busy in this round (named barrier 1 with an explicit
+// thread count, so idle warps of a partial round do not take part).  nthreads == 0 disables it.
+__device__ __forceinline__ void mjb_cta_sync(int nthreads) {
+  if (nthreads > 32) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool mjb_cta_any(int nthreads, bool pred) {
+  if (nthreads <= 32) return pred;
+  int out;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.s32 q, %2, 0;\n"
+      "bar.red.or.pred p, 1, %1, q;\n"
+      "selp.s32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(out)
+      : "r"(nthreads), "r"((int)pred)
+      : "memory");
+  return out != 0;
+}
+#define MJB_CTA_SYNC(nthreads) mjb_cta_sync(nthreads)
+#define MJB_CTA_ANY(nthreads, pred) mjb_cta_any((nthreads), (pred))
 #endif
 
 namespace mjb {
