@@ -309,3 +309,106 @@ def test_sensor_scene_C4_skipframes5_freejoint():
                 ref = np.concatenate([s.sensordata[oi["sensors"]], s.qpos, s.qvel])
                 assert rel_err(obs[e, i, :63][5:], ref[5:]) < 5 * RTOL, (t, e)
                 assert rel_err(obs[e, i, :5], ref[:5]) < 5e-3, (t, e, obs[e, i, :5], ref[:5])
+
+
+def test_single_env_squeezes_to_reference_shapes_and_wrappers():
+    """num_envs = 1 (the reference's only mode): numpy float64 observations, Python scalars, dict keys as the
+    reference returns them; the Gymnasium / Gym adapters on top (wrappers.py:12-142)."""
+    import os
+    from common import LEVELS
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    from mujoco_rl_environment_wrapper_b200.wrappers import GymnasiumWrapper, GymWrapper
+    from mujoco_rl_environment_wrapper_b200 import plugins as P
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "Ant.xml"), "agents": ["torso"], "maxSteps": 2,
+                    "rewardFunctions": [P.ant_reward_function]})
+    obs, infos = env.reset()
+    assert isinstance(obs["torso"], np.ndarray) and obs["torso"].dtype == np.float64 and obs["torso"].shape == (29,)
+    o, r, term, trunc, info = env.step({"torso": env.action_space("torso").sample()})
+    assert isinstance(r["torso"], float) and term == {"torso": False} and trunc == {"torso": False, "__all__": False}
+    assert info == {"torso": {}}
+    env.step({"torso": np.zeros(8, np.float32)})
+    *_, trunc, _ = env.step({"torso": np.zeros(8, np.float32)})
+    assert trunc["__all__"] is True                       # third call with maxSteps = 2
+    g = GymnasiumWrapper(env, "torso")
+    o, info = g.reset()
+    o, r, term, trunc, info = g.step(g.action_space.sample())
+    assert o.shape == (29,) and isinstance(term, bool) and trunc is False
+    o, r, done, info = GymWrapper(env, "torso").step(np.zeros(8, np.float32))
+    assert done is False
+    with pytest.raises(Exception, match="too many agents"):
+        two = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "agents": ["sender", "receiver"]})
+        GymnasiumWrapper(two, "sender")
+
+
+def test_user_plugins_run_as_batched_torch_code():
+    """Unknown plugins keep the reference's signatures (`dynamic(agent, actions)`, `f(env, agent)`) and run as
+    batched torch code after the kernel; fused and user plugins can be mixed."""
+    import os
+    from common import LEVELS
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    from mujoco_rl_environment_wrapper_b200 import plugins as P
+
+    class Echo:
+        def __init__(self, mujoco_gym):
+            self.mujoco_gym = mujoco_gym
+            self.observation_space = {"low": [-5, -5], "high": [5, 5]}
+            self.action_space = {"low": [-1, -1], "high": [1, 1]}
+
+        def dynamic(self, agent, actions):
+            env = self.mujoco_gym
+            a = torch.as_tensor(actions, dtype=torch.float32, device=env.device).reshape(env.num_envs, 2)
+            env.data_store[agent]["last"] = a
+            return a.sum(dim=1), 2 * a, a[:, 0] > 0.9, {"who": agent}
+
+    def height_reward(env, agent):
+        return env.batch.qpos[:, 2] if agent == "sender" else env.batch.qpos[:, 17]
+
+    def never_done(env, agent):
+        return torch.zeros(env.num_envs, dtype=torch.bool, device=env.device)
+
+    N = 8
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "agents": ["sender", "receiver"], "num_envs": N,
+                    "environmentDynamics": [P.Language, Echo], "rewardFunctions": [height_reward], "doneFunctions": [never_done]})
+    assert env.action_routing["dynamic"] == {"Language": [8, 9], "Echo": [9, 11]}
+    assert env.observation_space("sender").shape == (62,) and env.action_space("sender").shape == (11,)
+    env.reset()
+    act = torch.rand(N, 2, 11, device="cuda") * 2 - 1
+    act[:, :, 8] = torch.tensor([1.7, 2.2], device="cuda")
+    o, r, term, trunc, info = env.step(act)
+    assert o["sender"].shape == (N, 62)
+    assert torch.equal(o["sender"][:, 59], torch.zeros(N, device="cuda")) and torch.equal(o["receiver"][:, 59], torch.ones(N, device="cuda"))
+    assert torch.allclose(o["sender"][:, 60:62], 2 * act[:, 0, 9:11])
+    assert torch.allclose(r["sender"], act[:, 0, 9:11].sum(1) + env.batch.qpos[:, 2])
+    assert torch.equal(term["receiver"], act[:, 1, 9] > 0.9) and "__all__" in term
+    assert info["sender"]["Echo"] == {"who": "sender"} and info["sender"]["Language"] == {}
+    assert torch.equal(env.data_store["sender"]["last"], act[:, 0, 9:11])
+    assert torch.equal(env.data_store["receiver"]["utterance"], torch.full((N,), 2, dtype=torch.int32, device="cuda"))
+
+
+def test_queries_distance_collision_get_data_filter_by_tag():
+    """mujoco_parent.py:394-478 / mujoco_rl.py:355-395 on the batched env."""
+    import os
+    from common import LEVELS
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    N = 16
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
+                    "agents": ["sender", "receiver"], "num_envs": N})
+    env.reset()
+    tg = env.filter_by_tag("target")
+    assert [t["name"] for t in tg] == ["choice_1", "choice_2"] and tg[0]["type"] == "body" and tg[0]["tags"] == ["target"]
+    d = env.distance("sender", "choice_1")
+    ref = np.linalg.norm(np.array([-5.522553, 0.9194446, 1.0]) - np.array([7.02852, -2.071592, 0.4710507]))
+    assert torch.allclose(d, torch.full((N,), ref, device="cuda", dtype=torch.float32), rtol=1e-5)
+    assert not bool(env.collision("sender_geom", "choice_1_geom").any())
+    for _ in range(400):
+        env.step({a: torch.zeros(N, 8) for a in env.agents})
+    # settled: some ankle capsule of every ant touches the floor (geom 0 is the unnamed plane)
+    touching = torch.zeros(N, dtype=torch.bool, device="cuda")
+    for g in ("left_ankle_geom", "right_ankle_geom", "third_ankle_geom", "fourth_ankle_geom"):
+        touching |= env.collision(0, g)
+    assert bool(touching.all())
+    with pytest.raises(Exception, match="not found"):
+        env.collision("nope", "sender_geom")
+    assert env.get_data("sender")["mass"] == pytest.approx(5.0 * 4 / 3 * np.pi * 0.25 ** 3)
+    with pytest.raises(KeyError):
+        env.get_data("no_such_object")
