@@ -133,34 +133,44 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 10 ms on a thread (NVML), DURING the timed region."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.reasons, self.max_sm, self._stop, self._thr = index, [], set(), None, False, None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self._nv = None
+            return
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self._nv
+        while not self._stop:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+        self._stop = True
+        if self._thr:
+            self._thr.join(timeout=1.0)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
                 "samples": len(sm)}
 
 
@@ -229,13 +239,14 @@ def run_ours(args):
 
     # ---- end-to-end arm: C-ABI host-buffer call, pinned H2D / D2H inside the timed region
     h_act, h_obs, h_rew, h_term, h_trunc = b.host_arrays()
-    host_pool = pool[:4].cpu().numpy()
+    host_pool = pool[:4].cpu().numpy()        # this step's actions arrive from the policy in host memory
     for k in range(3):
-        b.step_host(np.ascontiguousarray(host_pool[k % 4]), h_obs, h_rew, h_term, h_trunc)
+        np.copyto(h_act, host_pool[k % 4]); b.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        b.step_host(host_pool[k % 4], h_obs, h_rew, h_term, h_trunc)
+        np.copyto(h_act, host_pool[k % 4])    # host-side write of the actions into the page-locked call buffer
+        b.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     e2e_ms = D.max_over_ranks(e2e_ms, dev)
@@ -249,6 +260,12 @@ def run_ours(args):
         m = env.model
         bytes_env = algorithmic_bytes_per_env_step(m.nq, m.nv, m.nu, m.nsensordata, A, act_dim, 60, b.layout.probe_count)
         peak, which = peaks()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("envs_per_gpu") == N:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         achieved = bytes_env * N / (kern_ms * 1e-3) / 1e9
         agent_steps = N * A * world
         out = {
@@ -260,7 +277,7 @@ def run_ours(args):
             "e2e": {"value": agent_steps / (e2e_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h_act.nbytes), "d2h_bytes_per_step": int(h_obs.nbytes + h_rew.nbytes + h_term.nbytes + h_trunc.nbytes)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": which, "algorithmic_bytes_per_env_step": bytes_env, "kernel_ms": kern_ms_max,
                          "note": "physics-on step is issue/latency bound (SURVEY 8d): see profiles/ for issue-slot and stall evidence"},
             "clocks": clk,
@@ -283,8 +300,8 @@ def run_ours(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     a = ap.parse_args()

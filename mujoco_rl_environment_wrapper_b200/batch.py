@@ -100,10 +100,14 @@ class Batch:
         L.check(self._lib.mjb_step_host(self._h, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data,
                                         term.ctypes.data, trunc.ctypes.data), "step_host")
 
-    def host_arrays(self):
+    def host_arrays(self, pinned=True):
+        """(actions, obs, reward, term, trunc) host arrays for step_host.  Page-locked by default: the library
+        then copies straight to / from them; pageable arrays work too (staged through pinned memory)."""
         lay, A, N = self.layout, self.spec.n_agents, self.num_envs
-        return (np.zeros((N, A, lay.act_stride), np.float32), np.zeros((N, A, lay.obs_stride), np.float32),
-                np.zeros((N, A), np.float32), np.zeros((N, A + 1), np.uint8), np.zeros((N, A + 1), np.uint8))
+        shapes = [((N, A, lay.act_stride), torch.float32), ((N, A, lay.obs_stride), torch.float32), ((N, A), torch.float32),
+                  ((N, A + 1), torch.uint8), ((N, A + 1), torch.uint8)]
+        self._host_keep = [torch.zeros(s, dtype=d, pin_memory=pinned) for s, d in shapes]
+        return tuple(t.numpy() for t in self._host_keep)
 
     @property
     def launch_count(self):

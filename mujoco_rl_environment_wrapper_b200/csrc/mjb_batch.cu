@@ -114,6 +114,7 @@ struct mjb_batch {
   int* h_first = nullptr;  // pinned: initial value of the work counter (= grid * warps)
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
+  const void* pin_cache[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -291,19 +292,33 @@ int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward,
   const size_t N = b->num_envs, A = dm.n_agents;
   const size_t nb_act = sizeof(float) * N * A * dm.act_stride, nb_obs = sizeof(float) * N * A * dm.obs_stride;
   const size_t nb_rew = sizeof(float) * N * A, nb_flag = N * (A + 1);
-  memcpy(b->h_act, actions, nb_act);
-  CUDA_TRY(cudaMemcpyAsync(b->B.actions, b->h_act, nb_act, cudaMemcpyHostToDevice, b->stream));
+  // page-locked caller buffers are copied directly; pageable ones go through the pinned staging area
+  auto pinned = [&](const void* p) {
+    if (p == b->pin_cache[0] || p == b->pin_cache[1] || p == b->pin_cache[2] || p == b->pin_cache[3] || p == b->pin_cache[4]) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool direct = pinned(actions) && pinned(obs) && pinned(reward) && pinned(term) && pinned(trunc);
+  if (direct) {
+    b->pin_cache[0] = actions; b->pin_cache[1] = obs; b->pin_cache[2] = reward; b->pin_cache[3] = term; b->pin_cache[4] = trunc;
+  } else {
+    memcpy(b->h_act, actions, nb_act);
+  }
+  CUDA_TRY(cudaMemcpyAsync(b->B.actions, direct ? actions : b->h_act, nb_act, cudaMemcpyHostToDevice, b->stream));
   int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr);
   if (rc != MJB_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(b->h_obs, b->B.obs, nb_obs, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(b->h_rew, b->B.reward, nb_rew, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(b->h_term, b->B.term, nb_flag, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(b->h_trunc, b->B.trunc, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(direct ? obs : b->h_obs, b->B.obs, nb_obs, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(direct ? reward : b->h_rew, b->B.reward, nb_rew, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(direct ? term : b->h_term, b->B.term, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(direct ? trunc : b->h_trunc, b->B.trunc, nb_flag, cudaMemcpyDeviceToHost, b->stream));
   CUDA_TRY(cudaStreamSynchronize(b->stream));
-  memcpy(obs, b->h_obs, nb_obs);
-  memcpy(reward, b->h_rew, nb_rew);
-  memcpy(term, b->h_term, nb_flag);
-  memcpy(trunc, b->h_trunc, nb_flag);
+  if (!direct) {
+    memcpy(obs, b->h_obs, nb_obs);
+    memcpy(reward, b->h_rew, nb_rew);
+    memcpy(term, b->h_term, nb_flag);
+    memcpy(trunc, b->h_trunc, nb_flag);
+  }
   return MJB_OK;
 }
 
