@@ -111,7 +111,7 @@ def run_reference(args):
     from oracle import build_oracle
     build_oracle()
     pool, cores = make_pool()
-    per_step_s = min(10.0, max(0.25, 90.0 / max(1, args.steps + args.warmup)))
+    per_step_s = min(10.0, max(0.05, 100.0 / max(1, args.steps + args.warmup)))
     vals = []
     for i in range(args.warmup + args.steps):
         v, n = cpu_arm(per_step_s, pool, cores)

@@ -7,8 +7,8 @@ Mirrors the reference's public surface (MuJoCo_Gym/mujoco_rl.py:18-430, mujoco_p
 `timestep`, `max_steps`, `skip_frames`, `action_routing`, `agents_action_index`,
 `agents_observation_index`.
 
-New optional config keys: `num_envs` (default 1), `device`, `seed`, `probes` (extra body / geom
-names whose positions are exported every step).  With `num_envs == 1` results are squeezed to the
+New optional config keys: `num_envs` (default 1), `device`, `seed`.  Positions of the agents' bodies and of
+the `filter_by_tag("target")` objects are exported every step (`distance`, `get_data`).  With `num_envs == 1` results are squeezed to the
 reference's shapes (numpy arrays, Python scalars); otherwise every per-agent value is a CUDA tensor
 with a leading `num_envs` dimension.  There is no CPU path: construction raises without a GPU.
 """
@@ -70,7 +70,6 @@ class MuJoCoRL:
         self.agent_cameras = config_dict.get("agentCameras", False)  # accepted, cameras are not observations
         self.num_envs = int(config_dict.get("num_envs", 1))
         self.seed = int(config_dict.get("seed", 1234))
-        self._extra_probes = list(config_dict.get("probes", []))
         dev = config_dict.get("device", None)
         if not torch.cuda.is_available():
             raise RuntimeError("MuJoCoRL (B200): no CUDA device available; this implementation has no CPU fallback")
@@ -409,8 +408,8 @@ class MuJoCoRL:
     def _position(self, name_or_xyz):
         if isinstance(name_or_xyz, str):
             if name_or_xyz not in self._probe_names:
-                raise Exception(f"'{name_or_xyz}' is not an exported position: add it to config_dict['probes'] "
-                                f"(exported: {self._probe_names})")
+                raise Exception(f"'{name_or_xyz}' is not an exported position (exported: {self._probe_names}; "
+                                f"agents and objects tagged 'target' in the info JSON)")
             return self._batch.probe[:, self._probe_names.index(name_or_xyz), :3]
         return torch.as_tensor(name_or_xyz, dtype=torch.float32, device=self.device).reshape(-1, 3)
 
