@@ -97,13 +97,20 @@ inline void host_jac(const ModelView& m, const HostKin& k, int body, V3 point, s
   }
 }
 
-// dense joint-space inertia (nv x nv, row-major), armature included
+// dense joint-space inertia (nv x nv, row-major), armature included.  Only the dofs on a body's chain
+// contribute to its Jacobian, so the double loop runs over that chain.
 inline void host_mass_matrix(const ModelView& m, const HostKin& k, std::vector<double>& M) {
   int nv = m.nv;
   M.assign((size_t)nv * nv, 0.0);
   std::vector<double> jp, jr;
+  std::vector<int> chain;
   for (int b = 1; b < m.nbody; b++) {
     double mass = m.body_mass[b];
+    if (mass <= 0) continue;
+    chain.clear();
+    for (int bb = b; bb > 0; bb = m.body_parentid[bb])
+      for (int d = m.body_dofadr[bb]; d >= 0 && d < m.body_dofadr[bb] + m.body_dofnum[bb]; d++) chain.push_back(d);
+    if (chain.empty()) continue;
     host_jac(m, k, b, k.xipos[b], jp, jr);
     // world inertia = R diag(I) R^T
     M3 R = k.ximat[b], Iw;
@@ -113,14 +120,15 @@ inline void host_mass_matrix(const ModelView& m, const HostKin& k, std::vector<d
         for (int a = 0; a < 3; a++) s += R(r, a) * m.body_inertia[3 * b + a] * R(c, a);
         Iw(r, c) = s;
       }
-    for (int i = 0; i < nv; i++)
-      for (int j = 0; j < nv; j++) {
-        double s = 0;
-        for (int r = 0; r < 3; r++) s += mass * jp[r * nv + i] * jp[r * nv + j];
-        for (int r = 0; r < 3; r++)
-          for (int c = 0; c < 3; c++) s += jr[r * nv + i] * Iw(r, c) * jr[c * nv + j];
+    for (int i : chain) {
+      double Ij[3];  // Iw * jr[:, i]
+      for (int r = 0; r < 3; r++) Ij[r] = Iw(r, 0) * jr[i] + Iw(r, 1) * jr[nv + i] + Iw(r, 2) * jr[2 * nv + i];
+      for (int j : chain) {
+        double s = mass * (jp[i] * jp[j] + jp[nv + i] * jp[nv + j] + jp[2 * nv + i] * jp[2 * nv + j]) +
+                   Ij[0] * jr[j] + Ij[1] * jr[nv + j] + Ij[2] * jr[2 * nv + j];
         M[(size_t)i * nv + j] += s;
       }
+    }
   }
   for (int i = 0; i < nv; i++) M[(size_t)i * nv + i] += m.dof_armature[i];
 }

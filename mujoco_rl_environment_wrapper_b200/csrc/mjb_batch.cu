@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(512, 1) k_env(const __grid_constant__ DevModel
   mbar_wait(bar, 0);
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
-  Ctx c{&dm, img, scratch, lane, probe, 0};
+  Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1};
   // dynamic env scheduling: per-env cost varies (contact count, Newton iterations), so every warp pulls
   // its next env from a grid-wide counter instead of owning a fixed slice
   // Two scheduling modes share ONE call site of the step code:
@@ -76,14 +76,14 @@ __global__ void __launch_bounds__(512, 1) k_env(const __grid_constant__ DevModel
   int env = blockIdx.x * warps + warp;
   for (int r = 0;; r++) {
     if (lockstep ? (r >= rounds) : (env >= num_envs)) break;
-    if (lockstep == 1) {
+    if (lockstep == 1 || lockstep == 3) {
       int busy = num_envs - (blockIdx.x * warps + r * stride);  // env-warps of this CTA with work in this round
       // (a masked reset lets warps skip their env, so intra-step alignment is off for it)
       c.cta_threads = (mask == nullptr ? 32 : 0) * (busy > warps ? warps : (busy < 0 ? 0 : busy));
     }
     if (env < num_envs) run_env(c, B, (lockstep && env_order) ? env_order[env] : env, mode, skip_frames, mask);
     if (lockstep) {
-      __syncthreads();
+      if (lockstep != 3) __syncthreads();   // mode 3 aligns inside the step (before the collision phase) instead
       env += stride;
     } else {
       __syncwarp();

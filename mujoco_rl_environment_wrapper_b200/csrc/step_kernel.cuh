@@ -85,6 +85,7 @@ struct Ctx {
   int lane;
   float* probe;         // exported positions of this env (shared memory, 4 floats per probe)
   int cta_threads;      // threads of the CTA busy in this lock-step round (0 / 32: no CTA-level alignment)
+  int align_all;        // 1: also align around constraints / Newton iterations; 0: only before the collision phase
 };
 #define CI(f) ((const int*)(c.img + c.dm->off[IF_##f]))
 #define CU(f) ((const uint32_t*)(c.img + c.dm->off[IF_##f]))
@@ -971,7 +972,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     float fn = wsum(lane < nv ? qfrc[lane] * qfrc[lane] + Ma[lane] * Ma[lane] : 0.f);
     if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) done = true;
     }
-    if (!MJB_CTA_ANY(c.cta_threads, !done)) break;
+    if (!(c.align_all ? MJB_CTA_ANY(c.cta_threads, !done) : !done)) break;
     if (done) continue;
     it++;
     // Hessian H = M + J' diag(D active) J (packed lower triangle)
@@ -1224,11 +1225,11 @@ MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out) {
   MJB_CTA_SYNC(c.cta_threads);  // re-align the env-warps of the CTA before the data-dependent phases
   int ncon = collide(c);
   if (sensors) sensors_pos(c);
-  MJB_CTA_SYNC(c.cta_threads);
+  if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
   make_constraints(c, ncon);
-  MJB_CTA_SYNC(c.cta_threads);
+  if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
   int it = newton(c, ncon);
-  MJB_CTA_SYNC(c.cta_threads);
+  if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
   if (iters_out) *iters_out = it;
   if (sensors) sensors_acc(c, ncon);
   return ncon;

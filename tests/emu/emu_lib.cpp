@@ -36,7 +36,7 @@ int emu_run(const void* blob, const mjb_env_spec* spec, int num_envs, const mjb_
     std::vector<float> scratch(img.dm.env_words + 64, 0.f), probe(4 * img.dm.nprobe + 4, 0.f);
     for (int env = 0; env < num_envs; env++) {
       simt::run_warp([&]() {
-        mjb::Ctx c{&img.dm, img.words.data(), scratch.data(), simt::lane(), probe.data(), 0};
+        mjb::Ctx c{&img.dm, img.words.data(), scratch.data(), simt::lane(), probe.data(), 0, 0};
         mjb::run_env(c, *B, env, mode, skip_frames, mask);
       }, reverse != 0);
     }
