@@ -67,6 +67,13 @@ class OracleSim:
         self._h = self._lib.orc_create(self._blob, len(self._blob))
         if not self._h:
             raise RuntimeError("oracle: could not create simulation from blob")
+        # fixed-size state arrays never move: cache the zero-copy views (as `MjData.qpos` etc. are in mujoco)
+        self._fixed = {n: self.array(n) for n in ("qpos", "qvel", "ctrl", "qacc", "qacc_warmstart", "sensordata", "xpos",
+                                                  "xmat", "xipos", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat")}
+        for n in ("xpos", "xipos", "geom_xpos", "site_xpos"):
+            self._fixed[n] = self._fixed[n].reshape(-1, 3)
+        for n in ("xmat", "geom_xmat", "site_xmat"):
+            self._fixed[n] = self._fixed[n].reshape(-1, 9)
 
     def __del__(self):
         try:
@@ -86,19 +93,19 @@ class OracleSim:
         return np.ctypeslib.as_array(p, shape=(n.value,))
 
     # state views (valid until the next call that resizes: efc_* arrays change size every forward)
-    qpos = property(lambda s: s.array("qpos"))
-    qvel = property(lambda s: s.array("qvel"))
-    ctrl = property(lambda s: s.array("ctrl"))
-    qacc = property(lambda s: s.array("qacc"))
-    qacc_warmstart = property(lambda s: s.array("qacc_warmstart"))
-    sensordata = property(lambda s: s.array("sensordata"))
-    xpos = property(lambda s: s.array("xpos").reshape(-1, 3))
-    xmat = property(lambda s: s.array("xmat").reshape(-1, 9))
-    xipos = property(lambda s: s.array("xipos").reshape(-1, 3))
-    geom_xpos = property(lambda s: s.array("geom_xpos").reshape(-1, 3))
-    geom_xmat = property(lambda s: s.array("geom_xmat").reshape(-1, 9))
-    site_xpos = property(lambda s: s.array("site_xpos").reshape(-1, 3))
-    site_xmat = property(lambda s: s.array("site_xmat").reshape(-1, 9))
+    qpos = property(lambda s: s._fixed["qpos"])
+    qvel = property(lambda s: s._fixed["qvel"])
+    ctrl = property(lambda s: s._fixed["ctrl"])
+    qacc = property(lambda s: s._fixed["qacc"])
+    qacc_warmstart = property(lambda s: s._fixed["qacc_warmstart"])
+    sensordata = property(lambda s: s._fixed["sensordata"])
+    xpos = property(lambda s: s._fixed["xpos"])
+    xmat = property(lambda s: s._fixed["xmat"])
+    xipos = property(lambda s: s._fixed["xipos"])
+    geom_xpos = property(lambda s: s._fixed["geom_xpos"])
+    geom_xmat = property(lambda s: s._fixed["geom_xmat"])
+    site_xpos = property(lambda s: s._fixed["site_xpos"])
+    site_xmat = property(lambda s: s._fixed["site_xmat"])
     time = property(lambda s: s._lib.orc_time(s._h))
     ncon = property(lambda s: s._lib.orc_ncon(s._h))
     nefc = property(lambda s: s._lib.orc_nefc(s._h))

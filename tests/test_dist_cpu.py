@@ -22,7 +22,7 @@ assert int(allst[:, 1].sum().item()) == 65537
 assert allst[:, 0].tolist() == [float(r) for r in range(world)]
 m = D.max_over_ranks(10.0 + rank, device="cpu")
 assert m == 10.0 + world - 1
-print("rank", rank, "ok")
+open(os.path.join(os.environ["MJB_OUT"], f"rank{rank}.ok"), "w").write("ok")
 """
 
 
@@ -39,9 +39,9 @@ def test_shard_range_partitions(total, world):
 def test_gloo_world_size_2(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, MJB_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, MJB_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MJB_OUT=str(tmp_path))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", str(script)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists(), res.stdout + res.stderr
