@@ -46,7 +46,7 @@ inline int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevImage& out) {
+inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevImage& out, bool lite = false) {
   DevModel& dm = out.dm;
   memset(&dm, 0, sizeof(dm));
   std::vector<uint32_t>& W = out.words;
@@ -402,11 +402,18 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   sizes[SF_vecA] = sizes[SF_vecB] = sizes[SF_vecC] = sizes[SF_vecD] = nv;
   sizes[SF_rk] = m.integrator == MJB_INT_RK4 ? (m.nq + 3 * nv) : 1;
   sizes[SF_sens] = std::max(1, m.nsensordata);
+  if (lite) {
+    // skipFrames = 0 ("literal" benchmark configuration): no physics pass ever runs in a step, so an env only
+    // needs its state rows and the epilogue staging area -> many more envs in flight per SM
+    for (int i = 0; i < SF_COUNT; i++)
+      if (i != SF_qpos && i != SF_qvel && i != SF_qacc && i != SF_ctrl && i != SF_qfrc && i != SF_sens && i != SF_J) sizes[i] = 0;
+    sizes[SF_J] = MJB_MAX_AGENTS * (MJB_STORE_I_COUNT + MJB_STORE_F_COUNT) + 64 + 4;
+  }
   // lifetime aliasing: the Hessian lives where cinert + crb were (dead once the bias forces are known),
   // the broad-phase candidate list where cvel + cacc are (dead between the bias pass and the sensors)
-  const bool alias_H = tri <= r4(sizes[SF_cinert]) + r4(sizes[SF_crb]);
+  const bool alias_H = !lite && tri <= r4(sizes[SF_cinert]) + r4(sizes[SF_crb]);
   if (dm.maxcand > r4(sizes[SF_cvel]) + r4(sizes[SF_cacc])) dm.maxcand = std::max(32, r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]) - 4);
-  const bool alias_cand = dm.maxcand <= r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]);
+  const bool alias_cand = !lite && dm.maxcand <= r4(sizes[SF_cvel]) + r4(sizes[SF_cacc]);
   // without acceleration-stage sensors nothing touches cvel / cacc after the bias pass: the contact
   // records can live there too (behind the candidate list)
   bool alias_con = false;
@@ -423,7 +430,7 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   {
     int used = 0;  // greedy: as many of the solver fields as fit into the dead region
     for (int f : solver_fields)
-      if (used + r4(sizes[f]) <= dead_words) { aliased[f] = true; used += r4(sizes[f]); }
+      if (!lite && used + r4(sizes[f]) <= dead_words) { aliased[f] = true; used += r4(sizes[f]); }
   }
   int off = 0;
   for (int i = 0; i < SF_COUNT; i++) {

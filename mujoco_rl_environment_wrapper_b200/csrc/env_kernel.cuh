@@ -155,6 +155,7 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
 }
 
 // whole per-env pipeline.  Every lane of the warp calls this with the same arguments.
+template <bool PHYS>
 MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int skip_frames, const uint8_t* reset_mask) {
   float* probe = c.probe;
   const DevModel& dm = *c.dm;
@@ -223,7 +224,8 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
   const int passes = integrate ? skip_frames : 1;
   int niter = 0;
   MJB_NOUNROLL
-  for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, &niter);
+  if (PHYS)
+    for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, &niter);
   if (ncon >= 0) {
     if (B.ncon && lane == 0) B.ncon[env] = ncon;
     if (B.niter && lane == 0) B.niter[env] = niter;

@@ -43,7 +43,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // One CTA per SM slot, `warps` environments in flight per CTA; each warp walks the env index space
 // with a grid-wide stride (envs are independent, no inter-warp communication after the staging).
-__global__ void __launch_bounds__(512, 1) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
+template <bool PHYS>
+__global__ void __launch_bounds__(512, PHYS ? 1 : 4) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
                       int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env,
                       int lockstep, const int* __restrict__ env_order) {
   extern __shared__ __align__(128) uint32_t smem[];
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(512, 1) k_env(const __grid_constant__ DevModel
       // (a masked reset lets warps skip their env, so intra-step alignment is off for it)
       c.cta_threads = (mask == nullptr ? 32 : 0) * (busy > warps ? warps : (busy < 0 ? 0 : busy));
     }
-    if (env < num_envs) run_env(c, B, (lockstep && env_order) ? env_order[env] : env, mode, skip_frames, mask);
+    if (env < num_envs) run_env<PHYS>(c, B, (lockstep && env_order) ? env_order[env] : env, mode, skip_frames, mask);
     if (lockstep) {
       if (lockstep != 3) __syncthreads();   // mode 3 aligns inside the step (before the collision phase) instead
       env += stride;
@@ -98,6 +99,10 @@ __global__ void __launch_bounds__(512, 1) k_env(const __grid_constant__ DevModel
 
 struct mjb_batch {
   mjb::DevImage img;
+  mjb::DevImage lite;     // skipFrames = 0 only: state-rows-only scratch layout for the step kernel
+  bool has_lite = false;
+  int lite_warps = 0, lite_grid = 0;
+  size_t lite_smem = 0;
   mjb_buffers B;
   int num_envs = 0, device = 0, warps = 0, grid = 0;
   size_t smem_bytes = 0;
@@ -138,10 +143,18 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
   int first = b->grid * b->warps;
   int* counter = b->d_next + b->next_slot;
   b->next_slot = (b->next_slot + 1) % 64;
-  CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  if (b->lockstep == 0)  // only the dynamic scheduler consumes the counter
+    CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, b->stream));
   (void)first;
-  mjb::k_env<<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode,
-                                                                     skip_frames, mask, counter, b->lockstep, b->lockstep ? b->env_order : nullptr);
+  if (mode == mjb::MODE_STEP && b->has_lite) {
+    // no physics in the step: many small envs per SM, rounds aligned the same way
+    mjb::k_env<false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, b->stream>>>(b->lite.dm, b->d_image, b->B, b->num_envs, mode,
+                                                                                      skip_frames, mask, counter, 2, nullptr);
+  } else {
+    mjb::k_env<true><<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode,
+                                                                             skip_frames, mask, counter, b->lockstep,
+                                                                             b->lockstep ? b->env_order : nullptr);
+  }
   CUDA_TRY(cudaGetLastError());
   if (b->timing) {
     CUDA_TRY(cudaEventRecord(e1, b->stream));
@@ -222,9 +235,26 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
   b->grid = (num_envs + warps - 1) / warps;
   if (b->grid > sms) b->grid = sms;
   b->smem_bytes = fixed + per_env * warps;
-  if (cudaFuncSetAttribute(mjb::k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(mjb::k_env<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes) != cudaSuccess) {
     mjb::set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(cudaGetLastError()));
     return fail(MJB_ERR_CUDA);
+  }
+  if (spec->skip_frames == 0) {
+    try {
+      mjb::ModelView mv(m->host.blob.data());
+      mjb::build_dev_model(mv, *spec, b->lite, /*lite=*/true);
+    } catch (const std::exception& e) { mjb::set_error(e.what()); return fail(MJB_ERR_LIMIT); }
+    size_t lite_env = ((size_t)b->lite.dm.env_words + 4 * ((b->lite.dm.nprobe + 3) & ~3)) * 4;
+    b->lite_warps = 16;
+    b->lite_smem = fixed + lite_env * b->lite_warps;
+    int per_sm = 1;
+    if (cudaFuncSetAttribute(mjb::k_env<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lite_smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mjb::k_env<false>, b->lite_warps * 32, b->lite_smem) != cudaSuccess || per_sm < 1) {
+      mjb::set_error("lite step kernel configuration failed");
+      return fail(MJB_ERR_CUDA);
+    }
+    b->lite_grid = std::min((num_envs + b->lite_warps - 1) / b->lite_warps, prop.multiProcessorCount * per_sm);
+    b->has_lite = true;
   }
   if (cudaMalloc(&b->d_image, (size_t)dm.image_words * 4) != cudaSuccess ||
       cudaMemcpy(b->d_image, b->img.words.data(), (size_t)dm.image_words * 4, cudaMemcpyHostToDevice) != cudaSuccess) {

@@ -37,7 +37,7 @@ int emu_run(const void* blob, const mjb_env_spec* spec, int num_envs, const mjb_
     for (int env = 0; env < num_envs; env++) {
       simt::run_warp([&]() {
         mjb::Ctx c{&img.dm, img.words.data(), scratch.data(), simt::lane(), probe.data(), 0, 0};
-        mjb::run_env(c, *B, env, mode, skip_frames, mask);
+        mjb::run_env<true>(c, *B, env, mode, skip_frames, mask);
       }, reverse != 0);
     }
     return 0;
