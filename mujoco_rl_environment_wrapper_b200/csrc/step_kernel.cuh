@@ -977,7 +977,13 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     it++;
     // Hessian H = M + J' diag(D active) J (packed lower triangle)
     MJB_NOUNROLL
-    for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) H[i] = M[i];
+    {
+      // both triangles start 16 B aligned and are padded to a multiple of 4 words: copy as 128-bit words
+      struct alignas(16) W4 { float a, b, c, d; };
+      const W4* src = (const W4*)M;
+      W4* dst = (W4*)H;
+      for (int i = lane; i < ((nv * (nv + 1)) / 2 + 3) / 4; i += 32) dst[i] = src[i];
+    }
     MJB_SYNC();
     MJB_NOUNROLL
     for (int k = lane; k < dm.nlim; k += 32) {
@@ -1140,6 +1146,12 @@ MJB_DEV void sensors_pos(const Ctx& c) {
         int gb = CI(geom_mb)[g];
         if ((gb >= 0 && gb == bex) || !CI(geom_ray)[g]) continue;
         GeomW gw = geom_world(c, g);
+        if (gw.type != MJB_GEOM_PLANE) {
+          // conservative bounding-sphere rejection (the ray direction is a unit vector)
+          f3 mvec = gw.pos - pnt;
+          float rb = CF(geom_rbound)[g], tca = dot(mvec, vec), mm = dot(mvec, mvec);
+          if (mm - tca * tca > rb * rb || (tca < 0.f && mm > rb * rb)) continue;
+        }
         float x = ray_geom(gw.pos, gw.mat, gw.size, pnt, vec, gw.type);
         if (x >= 0 && x < best) best = x;
       }

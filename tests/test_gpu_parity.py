@@ -165,6 +165,16 @@ def test_full_size_properties():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert bool((outs[0][0] == outs[0][0][0:1]).all()) and bool((outs[0][1] == outs[0][1][0:1]).all())
     assert bool(torch.isfinite(outs[0][0]).all())
+    # contact slots: a 400-step random rollout of 65536 envs never fills the per-env contact table
+    g2 = torch.Generator(device="cuda"); g2.manual_seed(1)
+    worst = 0
+    for k in range(400):
+        b.actions[:, :, :8] = torch.rand((N, 2, 8), generator=g2, device="cuda") * 2 - 1
+        b.physics(1)
+        if k % 20 == 19:
+            worst = max(worst, int(b.ncon.max()))
+    assert 0 < worst < b.layout.maxcon, worst
+    assert bool(torch.isfinite(b.qpos).all()) and bool(torch.isfinite(b.qvel).all())
     b.reset(); b.sync(); q1 = b.qpos.clone(); b.reset(); b.sync()
     assert torch.equal(q1, b.qpos)
     mask = torch.zeros(N, dtype=torch.uint8, device="cuda"); mask[::2] = 1
