@@ -422,3 +422,46 @@ def test_queries_distance_collision_get_data_filter_by_tag():
     assert env.get_data("sender")["mass"] == pytest.approx(5.0 * 4 / 3 * np.pi * 0.25 ** 3)
     with pytest.raises(KeyError):
         env.get_data("no_such_object")
+
+
+def test_inter_ant_contacts_couple_the_trees():
+    """Two ants dropped onto each other: contacts between the two kinematic trees make the Newton Hessian a
+    single 28 x 28 block (shared-memory factorisation path instead of the per-tree register path) and exercise
+    capsule-capsule / sphere-capsule pairs across agents.  One step from identical states vs the oracle."""
+    model, tables, agents, fj = load_scene("2A")
+    spec, keep = make_spec(model, tables, agents, fj)
+    sim = OracleSim(model.blob)
+    rng = np.random.default_rng(21)
+    idx = np.array(tables.agents_action_index["sender"] + tables.agents_action_index["receiver"])
+    states, cross = [], 0
+    geom_body = model.fields["geom_bodyid"]
+    root = model.fields["body_rootid"]
+    for trial in range(24):
+        sim.reset()
+        # receiver straight above the sender, slightly offset and yawed, then let them fall together
+        sim.qpos[15:18] = sim.qpos[0:3] + np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), 0.45 + 0.2 * rng.random()])
+        yaw = rng.uniform(0, np.pi)
+        sim.qpos[18:22] = [np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
+        for t in range(260):
+            c = rng.uniform(-1, 1, 16)
+            sim.ctrl[idx] = c
+            if t >= 60 and t % 10 == 0:
+                pre = (sim.qpos.copy(), sim.qvel.copy(), sim.qacc_warmstart.copy(), sim.ctrl.copy(), c.reshape(2, 8).copy())
+                sim.step()
+                pairs = sim.contact_pairs()
+                ncross = sum(1 for a, b in pairs if root[geom_body[a]] != root[geom_body[b]] and root[geom_body[a]] and root[geom_body[b]])
+                cross += ncross > 0
+                states.append((pre, {"qpos": sim.qpos.copy(), "qvel": sim.qvel.copy(), "pairs": sorted(pairs)}))
+            else:
+                sim.step()
+    assert cross > 40, cross          # the sample really contains inter-tree contacts
+    b = _batch(model, spec, len(states), keep)
+    _upload(b, states, model, 8)
+    b.physics(1); b.sync()
+    q, v = b.qpos.cpu().numpy(), b.qvel.cpu().numpy()
+    ncon, cg = b.ncon.cpu().numpy(), b.contact_geom.cpu().numpy()
+    assert int(ncon.max()) < b.layout.maxcon
+    for e, (pre, post) in enumerate(states):
+        assert rel_err(q[e, :30], post["qpos"]) < RTOL, e
+        assert rel_err(v[e, :28], post["qvel"]) < RTOL, e
+        assert sorted((int(a), int(c_)) for a, c_ in cg[e, :ncon[e]]) == post["pairs"], e
