@@ -13,6 +13,7 @@
 #include "hmath.h"
 #include "host_kin.h"
 #include "model_view.h"
+#include "replicate.h"
 
 namespace mjb {
 
@@ -46,7 +47,7 @@ inline int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevImage& out, bool lite = false) {
+inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevImage& out, bool lite = false, int pack = 1) {
   DevModel& dm = out.dm;
   memset(&dm, 0, sizeof(dm));
   std::vector<uint32_t>& W = out.words;
@@ -378,8 +379,9 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
     dm.ldj = widest | 1;  // odd stride: lane = row accesses stay bank-conflict free
   }
   // ---- limits on per-env scratch
-  int dflt_con = ngdyn >= 16 ? 12 : 8;
-  dm.maxcon = std::max(1, env_int("MJB_MAXCON", dflt_con));
+  int dflt_con = (ngdyn / pack) >= 16 ? 12 : 8;
+  dm.maxcon1 = std::max(1, env_int("MJB_MAXCON", dflt_con));
+  dm.maxcon = dm.maxcon1 * pack;
   dm.maxcand = std::max(32, std::min(m.npair, env_int("MJB_MAXCAND", 160)));
   dm.maxefc = 2 * dm.nlim + 4 * dm.maxcon;
 
@@ -450,15 +452,75 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   // ---- HBM row strides (16-byte aligned rows)
   int max_obs = 1;
   for (int a = 0; a < spec.n_agents; a++) max_obs = std::max(max_obs, spec.obs_dim[a]);
-  dm.qpos_stride = r4(m.nq); dm.qvel_stride = r4(m.nv); dm.ctrl_stride = r4(std::max(1, m.nu));
-  dm.sensor_stride = r4(std::max(1, m.nsensordata)); dm.act_stride = r4(std::max(1, spec.act_dim));
+  dm.pack = pack; dm.a1 = spec.n_agents / pack; dm.t1 = spec.n_targets / pack; dm.nq1 = m.nq / pack; dm.nv1 = m.nv / pack;
+  dm.nu1 = m.nu / pack; dm.ns1 = m.nsensordata / pack; dm.np1 = dm.nprobe / pack; dm.ngeom1 = m.ngeom / pack;
+  dm.qpos_stride = r4(dm.nq1); dm.qvel_stride = r4(dm.nv1); dm.ctrl_stride = r4(std::max(1, dm.nu1));
+  dm.sensor_stride = r4(std::max(1, dm.ns1)); dm.act_stride = r4(std::max(1, spec.act_dim));
   dm.obs_stride = r4(max_obs); dm.store_i32 = MJB_STORE_I_COUNT; dm.store_f32 = MJB_STORE_F_COUNT;
 }
 
 inline void fill_layout(const DevModel& dm, int num_envs, mjb_layout& L) {
   L.num_envs = num_envs; L.qpos_stride = dm.qpos_stride; L.qvel_stride = dm.qvel_stride; L.ctrl_stride = dm.ctrl_stride;
   L.sensor_stride = dm.sensor_stride; L.act_stride = dm.act_stride; L.obs_stride = dm.obs_stride;
-  L.probe_count = dm.nprobe; L.maxcon = dm.maxcon; L.store_i32 = dm.store_i32; L.store_f32 = dm.store_f32;
+  L.probe_count = dm.np1; L.maxcon = dm.maxcon1; L.store_i32 = dm.store_i32; L.store_f32 = dm.store_f32;
+}
+
+
+// ---- env packing: K real envs per warp through a K-fold replicated model + a matching virtual env spec ----
+struct PackedModel {
+  int K = 1;
+  HostModel rep;                       // replicated model (K >= 2 only)
+  std::vector<int32_t> act_index, obs_index;
+  mjb_env_spec vspec;
+};
+
+// how many real envs share one warp: as many copies as fit the lane / agent / target limits
+inline int choose_pack(const HostModel& host, const mjb_env_spec& spec, int num_envs) {
+  int nv = host.get_int("nv");
+  int K = 32 / std::max(1, nv);
+  if (spec.n_agents > 0) K = std::min(K, MJB_MAX_AGENTS / spec.n_agents);
+  if (spec.n_targets > 0) K = std::min(K, MJB_MAX_TARGETS / spec.n_targets);
+  K = std::min(K, env_int("MJB_PACK", 4));
+  K = std::min(K, num_envs);
+  if (spec.skip_frames == 0) K = 1;   // no physics in the step: nothing to share
+  return std::max(1, K);
+}
+
+inline void make_packed(const HostModel& host, const mjb_env_spec& spec, int K, PackedModel& out) {
+  out.K = K;
+  out.vspec = spec;
+  if (K <= 1) return;
+  replicate_model(host, K, out.rep);
+  const int nq = host.get_int("nq"), nv = host.get_int("nv"), nu = host.get_int("nu"), ns = host.get_int("nsensordata"),
+            nbody = host.get_int("nbody"), ngeom = host.get_int("ngeom");
+  mjb_env_spec& v = out.vspec;
+  const int A = spec.n_agents, T = spec.n_targets, n_act = A * spec.n_phys_act, n_obs = spec.obs_adr[A];
+  v.n_agents = A * K; v.n_targets = T * K;
+  out.act_index.clear(); out.obs_index.clear();
+  for (int c = 0; c < K; c++) {
+    for (int a = 0; a < A; a++) {
+      v.obs_dim[c * A + a] = spec.obs_dim[a];
+      int b = spec.agent_body[a];
+      v.agent_body[c * A + a] = b <= 0 ? b : 1 + c * (nbody - 1) + (b - 1);
+      v.obs_adr[c * A + a] = c * n_obs + spec.obs_adr[a];
+    }
+    for (int i = 0; i < n_act; i++) out.act_index.push_back(spec.act_index[i] + c * (spec.free_joint ? nv : nu));
+    for (int i = 0; i < n_obs; i++) {
+      int e = spec.obs_index[i], kind = e >> 24, adr = e & 0xffffff;
+      adr += c * (kind == 0 ? ns : (kind == 1 ? nq : nv));
+      out.obs_index.push_back((kind << 24) | adr);
+    }
+    for (int t = 0; t < T; t++) {
+      v.target_objtype[c * T + t] = spec.target_objtype[t];
+      int id = spec.target_objid[t];
+      v.target_objid[c * T + t] = spec.target_objtype[t] == MJB_OBJ_BODY ? (id <= 0 ? id : 1 + c * (nbody - 1) + (id - 1)) : id + c * ngeom;
+    }
+  }
+  v.obs_adr[A * K] = K * n_obs;
+  if (out.act_index.empty()) out.act_index.push_back(0);
+  if (out.obs_index.empty()) out.obs_index.push_back(0);
+  v.act_index = out.act_index.data();
+  v.obs_index = out.obs_index.data();
 }
 
 }  // namespace mjb

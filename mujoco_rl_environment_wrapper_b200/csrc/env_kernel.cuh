@@ -25,10 +25,11 @@ MJB_DEV float probe_dist(const float* probe, int a, int b) {
 
 // the dynamics / reward / done programme of one env, executed by one lane in the reference's order
 // (dynamic outer, agent inner; then reward fn outer, agent inner; truncation; done fns with early exit)
-MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_reset, const float* probe, int* si, float* sf,
-                         const float* act, int* ts_io) {
+MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, int copy, bool is_reset, const float* probe, int* si,
+                         float* sf, const float* act, int* ts_io) {
+  // `env` is the REAL environment, `copy` its slot inside the (possibly packed) virtual env of this warp
   const DevModel& dm = *c.dm;
-  const int A = dm.n_agents;
+  const int A = dm.a1, ab = copy * dm.a1, tb = copy * dm.t1, n_targets = dm.t1;
   float* obs = B.obs + (size_t)env * A * dm.obs_stride;
   float* rew = B.reward + (size_t)env * A;
   uint8_t* term = B.term + (size_t)env * (A + 1);
@@ -45,7 +46,7 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
       for (int k = 0; k < dm.store_f32; k++) sf[a * dm.store_f32 + k] = 0.f;
     }
   MJB_NOUNROLL
-  for (int a = 0; a < A; a++) { reward[a] = 0.f; done[a] = false; opos[a] = dm.obs_adr[a + 1] - dm.obs_adr[a]; }
+  for (int a = 0; a < A; a++) { reward[a] = 0.f; done[a] = false; opos[a] = dm.obs_adr[ab + a + 1] - dm.obs_adr[ab + a]; }
   MJB_NOUNROLL
   for (int p = 0; p < dm.n_dynamics; p++) {
     const DevPlugin& dyn = dm.dynamics[p];
@@ -63,20 +64,20 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
         oa[opos[a]++] = val;
       } else if (dyn.kind == MJB_DYN_PICKUP) {
         int tgt = sia[MJB_STORE_I_TARGET];
-        if (tgt == 0 && dm.n_targets > 0) {
-          tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)dm.n_targets);
+        if (tgt == 0 && n_targets > 0) {
+          tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)n_targets);
           sia[MJB_STORE_I_TARGET] = tgt;
         }
         if (tgt > 0) {
-          float d = probe_dist(probe, dm.agent_probe[a], dm.target_probe[tgt - 1]);
+          float d = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
           if (d < dyn.param[0]) {
             sia[MJB_STORE_I_INVENTORY] ^= 1;
             reward[a] += 1.f;
-            tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)dm.n_targets);
+            tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)n_targets);
             sia[MJB_STORE_I_TARGET] = tgt;
-            sfa[MJB_STORE_F_DISTANCE] = probe_dist(probe, dm.agent_probe[a], dm.target_probe[tgt - 1]);
+            sfa[MJB_STORE_F_DISTANCE] = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
           }
-          const float* tp = probe + 4 * dm.target_probe[tgt - 1];
+          const float* tp = probe + 4 * dm.target_probe[tb + tgt - 1];
           oa[opos[a]] = tp[0]; oa[opos[a] + 1] = tp[1]; oa[opos[a] + 2] = tp[2];
         } else {
           oa[opos[a]] = 0.f; oa[opos[a] + 1] = 0.f; oa[opos[a] + 2] = 0.f;
@@ -109,24 +110,24 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
       float* sfa = sf + a * dm.store_f32;
       if (rf.kind == MJB_REW_TAG_DISTANCE) {
         int tgt = sia[MJB_STORE_I_TARGET];
-        if (dm.n_targets <= 0) continue;
+        if (n_targets <= 0) continue;
         if (tgt == 0) {
-          tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)dm.n_targets);
+          tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)n_targets);
           sia[MJB_STORE_I_TARGET] = tgt;
-          sfa[MJB_STORE_F_DISTANCE] = probe_dist(probe, dm.agent_probe[a], dm.target_probe[tgt - 1]);
+          sfa[MJB_STORE_F_DISTANCE] = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
         } else {
-          float d = probe_dist(probe, dm.agent_probe[a], dm.target_probe[tgt - 1]);
+          float d = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
           reward[a] += (sfa[MJB_STORE_F_DISTANCE] - d) * rf.param[0];
           sfa[MJB_STORE_F_DISTANCE] = d;
         }
       } else if (rf.kind == MJB_REW_ANT) {
-        float x_after = probe[4 * dm.agent_probe[a]];
+        float x_after = probe[4 * dm.agent_probe[ab + a]];
         if (!sia[MJB_STORE_I_HAS_XPOS]) {
           sia[MJB_STORE_I_HAS_XPOS] = 1;
         } else {
           float cc = 0.f;
           MJB_NOUNROLL
-          for (int u = 0; u < dm.nu; u++) cc += SF(ctrl)[u] * SF(ctrl)[u];
+          for (int u = 0; u < dm.nu1; u++) cc += SF(ctrl)[copy * dm.nu1 + u] * SF(ctrl)[copy * dm.nu1 + u];
           // contact cost term: cfrc_ext is zero on these models (no force/acc sensors), SURVEY Q11
           reward[a] += (x_after - sfa[MJB_STORE_F_XPOS_BEFORE]) / dm.timestep - 0.5f * cc;
         }
@@ -154,65 +155,97 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, bool is_re
   *ts_io = ts + 1;
 }
 
-// whole per-env pipeline.  Every lane of the warp calls this with the same arguments.
-template <bool PHYS>
-MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int skip_frames, const uint8_t* reset_mask) {
+// element i of a virtual per-copy array -> (copy, element); no division in the unpacked case
+MJB_DEV void split_copy(int i, int n1, int K, int& k, int& j) {
+  if (K == 1) { k = 0; j = i; }
+  else { k = i / n1; j = i - k * n1; }
+}
+
+// whole per-env pipeline.  Every lane of the warp calls this with the same arguments.  `venv` is the virtual
+// environment of this warp: dm.pack real environments (venv * pack + copy) presented to the physics as one
+// model with `pack` independent copies (csrc/replicate.h); pack == 1 is the plain case.  Virtual state index i
+// of a per-copy array of length n1 maps to copy i / n1, element i % n1 of that real env's HBM row.
+template <bool PHYS, bool PACKED>
+MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs, int mode, int skip_frames,
+                     const uint8_t* reset_mask) {
   float* probe = c.probe;
   const DevModel& dm = *c.dm;
-  const int lane = c.lane;
-  if (mode == MODE_RESET && reset_mask && !reset_mask[env]) return;
+  const int lane = c.lane, K = PACKED ? dm.pack : 1, e0 = venv * K;   // K == 1 folds all copy arithmetic away
+  // which copies hold a real env, and which of them this launch updates
+  uint32_t live = 0, upd = 0;
+  for (int k = 0; k < K; k++)
+    if (e0 + k < num_envs) {
+      live |= 1u << k;
+      if (!(mode == MODE_RESET && reset_mask && !reset_mask[e0 + k])) upd |= 1u << k;
+    }
+  if (!upd) return;
   float *qpos = SF(qpos), *qvel = SF(qvel), *qacc = SF(qacc), *ctrl = SF(ctrl), *sens = SF(sens);
-  float* g_qpos = B.qpos + (size_t)env * dm.qpos_stride;
-  float* g_qvel = B.qvel + (size_t)env * dm.qvel_stride;
-  float* g_ctrl = B.ctrl + (size_t)env * dm.ctrl_stride;
-  float* g_warm = B.warmstart + (size_t)env * dm.qvel_stride;
-  float* g_sens = B.sensordata + (size_t)env * dm.sensor_stride;
-  float* g_probe = B.probe + (size_t)env * dm.nprobe * 4;
-  if (mode == MODE_RESET) {
-    MJB_NOUNROLL
-    for (int i = lane; i < dm.nq; i += 32) qpos[i] = CF(qpos0)[i];
-    MJB_NOUNROLL
-    for (int i = lane; i < dm.nv; i += 32) { qvel[i] = 0.f; qacc[i] = 0.f; }
-    MJB_NOUNROLL
-    for (int i = lane; i < dm.nu; i += 32) ctrl[i] = 0.f;
-  } else {
-    MJB_NOUNROLL
-    for (int i = lane; i < dm.nq; i += 32) qpos[i] = g_qpos[i];
-    MJB_NOUNROLL
-    for (int i = lane; i < dm.nv; i += 32) { qvel[i] = g_qvel[i]; qacc[i] = g_warm[i]; }
-    MJB_NOUNROLL
-    for (int i = lane; i < dm.nu; i += 32) ctrl[i] = g_ctrl[i];
+  auto fresh = [&](int k) { return mode == MODE_RESET && ((upd >> k) & 1u); };   // copy starts from qpos0
+  auto has = [&](int k) { return ((live >> k) & 1u) != 0; };
+  MJB_NOUNROLL
+  for (int i = lane; i < dm.nq; i += 32) {
+    int k, j;
+    split_copy(i, dm.nq1, K, k, j);
+    qpos[i] = (fresh(k) || !has(k)) ? CF(qpos0)[i] : B.qpos[(size_t)(e0 + k) * dm.qpos_stride + j];
   }
   MJB_NOUNROLL
-  // the plugin store, this env's step counter and the dynamic actions are fetched now so that their
-  // global-memory latency hides behind the physics; they are consumed by the epilogue
-  const int A_ = dm.n_agents;
+  for (int i = lane; i < dm.nv; i += 32) {
+    int k, j;
+    split_copy(i, dm.nv1, K, k, j);
+    bool z = fresh(k) || !has(k);
+    qvel[i] = z ? 0.f : B.qvel[(size_t)(e0 + k) * dm.qvel_stride + j];
+    qacc[i] = z ? 0.f : B.warmstart[(size_t)(e0 + k) * dm.qvel_stride + j];
+  }
+  MJB_NOUNROLL
+  for (int i = lane; i < dm.nu; i += 32) {
+    int k, j;
+    split_copy(i, dm.nu1, K, k, j);
+    ctrl[i] = (fresh(k) || !has(k)) ? 0.f : B.ctrl[(size_t)(e0 + k) * dm.ctrl_stride + j];
+  }
+  MJB_NOUNROLL
+  for (int i = lane; i < dm.nsensordata; i += 32) {
+    int k, j;
+    split_copy(i, dm.ns1, K, k, j);
+    sens[i] = (fresh(k) || !has(k)) ? 0.f : B.sensordata[(size_t)(e0 + k) * dm.sensor_stride + j];
+  }
+  // exported positions: virtual probe order is [agents of every copy ..., targets of every copy ...]
+  auto probe_slot = [&](int p, int& k, int& p1) {
+    if (K == 1) { k = 0; p1 = p; }
+    else if (p < K * dm.a1) { k = p / dm.a1; p1 = p - k * dm.a1; }
+    else { int q = p - K * dm.a1; k = q / dm.t1; p1 = dm.a1 + (q - k * dm.t1); }
+  };
+  MJB_NOUNROLL
+  for (int i = lane; i < 4 * dm.nprobe; i += 32) {
+    int k, p1;
+    probe_slot(i >> 2, k, p1);
+    probe[i] = has(k) ? B.probe[((size_t)(e0 + k) * dm.np1 + p1) * 4 + (i & 3)] : 0.f;
+  }
+  // unpacked case: fetch the plugin store rows, dynamic actions and step counter of the env now, so that their
+  // global-memory latency overlaps the state loads / the physics; consumed by the epilogue
   const bool epi = (mode == MODE_STEP || mode == MODE_RESET);
-  int pre_si[2] = {0, 0};
+  int pre_si[2] = {0, 0}, pre_ts = 0;
   float pre_sf = 0.f, pre_act[2] = {0.f, 0.f};
-  int pre_ts = 0;
-  if (epi) {
-    const int* gsi = B.store_i + (size_t)env * A_ * dm.store_i32;
-    const float* gsf = B.store_f + (size_t)env * A_ * dm.store_f32;
-    const float* gact = B.actions + (size_t)env * A_ * dm.act_stride;
+  if (epi && K == 1) {
+    const int* gsi = B.store_i + (size_t)e0 * dm.a1 * dm.store_i32;
+    const float* gsf = B.store_f + (size_t)e0 * dm.a1 * dm.store_f32;
+    const float* gact = B.actions + (size_t)e0 * dm.a1 * dm.act_stride;
     for (int r = 0; r < 2; r++) {
       int i = lane + 32 * r;
-      if (i < A_ * dm.store_i32) pre_si[r] = gsi[i];
-      if (i < A_ * dm.act_stride) pre_act[r] = gact[i];
+      if (i < dm.a1 * dm.store_i32) pre_si[r] = gsi[i];
+      if (i < dm.a1 * dm.act_stride) pre_act[r] = gact[i];
     }
-    if (lane < A_ * dm.store_f32) pre_sf = gsf[lane];
-    if (lane == 0) pre_ts = B.timestep[env];
+    if (lane < dm.a1 * dm.store_f32) pre_sf = gsf[lane];
+    if (lane == 0) pre_ts = B.timestep[e0];
   }
-  for (int i = lane; i < dm.nsensordata; i += 32) sens[i] = mode == MODE_RESET ? 0.f : g_sens[i];
-  MJB_NOUNROLL
-  for (int i = lane; i < 4 * dm.nprobe; i += 32) probe[i] = g_probe[i];
   MJB_SYNC();
   if (mode == MODE_STEP || mode == MODE_PHYSICS) {
     // apply_action (mujoco_parent.py:316-332): overwrite qvel (freeJoint) or ctrl
-    const float* act = B.actions + (size_t)env * dm.n_agents * dm.act_stride;
     MJB_NOUNROLL
     for (int i = lane; i < dm.n_agents * dm.n_phys_act; i += 32) {
-      float v = act[(i / dm.n_phys_act) * dm.act_stride + (i % dm.n_phys_act)];
+      int av = i / dm.n_phys_act, k, a1;
+      split_copy(av, dm.a1, K, k, a1);
+      if (!has(k)) continue;
+      float v = B.actions[((size_t)(e0 + k) * dm.a1 + a1) * dm.act_stride + (i - av * dm.n_phys_act)];
       int idx = CI(act_index)[i];
       if (dm.free_joint) qvel[idx] = v; else ctrl[idx] = v;
     }
@@ -223,14 +256,15 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
   const bool integrate = !(mode == MODE_FORWARD || mode == MODE_RESET);
   const int passes = integrate ? skip_frames : 1;
   int niter = 0;
-  MJB_NOUNROLL
-  if (PHYS)
+  if (PHYS) {
+    MJB_NOUNROLL
     for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, &niter);
-  if (ncon >= 0) {
-    if (B.ncon && lane == 0) B.ncon[env] = ncon;
-    if (B.niter && lane == 0) B.niter[env] = niter;
+  }
+  if (ncon >= 0 && (B.ncon || B.contact_geom) && K == 1) {
+    const uint32_t* pairs = CU(pair_pack);
+    if (B.ncon && lane == 0) B.ncon[e0] = ncon;
+    if (B.niter && lane == 0) B.niter[e0] = niter;
     if (B.contact_geom) {
-      const uint32_t* pairs = CU(pair_pack);
       MJB_NOUNROLL
       for (int k = lane; k < dm.maxcon; k += 32) {
         int g1 = -1, g2 = -1;
@@ -240,55 +274,123 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int env, int mode, int 
           uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
           g1 = pk & 0xfff; g2 = (pk >> 12) & 0xfff; dist = r[CON_DIST];
         }
-        B.contact_geom[((size_t)env * dm.maxcon + k) * 2] = g1;
-        B.contact_geom[((size_t)env * dm.maxcon + k) * 2 + 1] = g2;
-        if (B.contact_dist) B.contact_dist[(size_t)env * dm.maxcon + k] = dist;
+        B.contact_geom[((size_t)e0 * dm.maxcon + k) * 2] = g1;
+        B.contact_geom[((size_t)e0 * dm.maxcon + k) * 2 + 1] = g2;
+        if (B.contact_dist) B.contact_dist[(size_t)e0 * dm.maxcon + k] = dist;
       }
+    }
+  } else if (ncon >= 0 && (B.ncon || B.contact_geom)) {
+    // packed: contact records per real env; a contact belongs to the copy its first geom lives in
+    const uint32_t* pairs = CU(pair_pack);
+    MJB_NOUNROLL
+    for (int k = lane; k < K; k += 32) {
+      if (!((upd >> k) & 1u)) continue;
+      int n = 0;
+      MJB_NOUNROLL
+      for (int i = 0; i < ncon; i++) {
+        const float* r = SF(con) + CON_STRIDE * i;
+        uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
+        int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
+        if (g1 / dm.ngeom1 != k) continue;
+        if (n < dm.maxcon1 && B.contact_geom) {
+          size_t o = (size_t)(e0 + k) * dm.maxcon1 + n;
+          B.contact_geom[2 * o] = g1 - k * dm.ngeom1; B.contact_geom[2 * o + 1] = g2 - k * dm.ngeom1;
+          if (B.contact_dist) B.contact_dist[o] = r[CON_DIST];
+        }
+        n++;
+      }
+      if (B.contact_geom)
+        for (int i = n; i < dm.maxcon1; i++) {
+          size_t o = (size_t)(e0 + k) * dm.maxcon1 + i;
+          B.contact_geom[2 * o] = -1; B.contact_geom[2 * o + 1] = -1;
+          if (B.contact_dist) B.contact_dist[o] = 0.f;
+        }
+      if (B.ncon) B.ncon[e0 + k] = n < dm.maxcon1 ? n : dm.maxcon1;
+      if (B.niter) B.niter[e0 + k] = niter;
     }
   }
   MJB_SYNC();
+  auto writes = [&](int k) { return ((upd >> k) & 1u) != 0; };
   MJB_NOUNROLL
-  for (int i = lane; i < dm.nq; i += 32) g_qpos[i] = qpos[i];
+  for (int i = lane; i < dm.nq; i += 32) {
+    int k, j;
+    split_copy(i, dm.nq1, K, k, j);
+    if (writes(k)) B.qpos[(size_t)(e0 + k) * dm.qpos_stride + j] = qpos[i];
+  }
   MJB_NOUNROLL
-  for (int i = lane; i < dm.nv; i += 32) { g_qvel[i] = qvel[i]; g_warm[i] = qacc[i]; }
+  for (int i = lane; i < dm.nv; i += 32) {
+    int k, j;
+    split_copy(i, dm.nv1, K, k, j);
+    if (writes(k)) { B.qvel[(size_t)(e0 + k) * dm.qvel_stride + j] = qvel[i]; B.warmstart[(size_t)(e0 + k) * dm.qvel_stride + j] = qacc[i]; }
+  }
   MJB_NOUNROLL
-  for (int i = lane; i < dm.nu; i += 32) g_ctrl[i] = ctrl[i];
+  for (int i = lane; i < dm.nu; i += 32) {
+    int k, j;
+    split_copy(i, dm.nu1, K, k, j);
+    if (writes(k)) B.ctrl[(size_t)(e0 + k) * dm.ctrl_stride + j] = ctrl[i];
+  }
   MJB_NOUNROLL
-  for (int i = lane; i < dm.nsensordata; i += 32) g_sens[i] = sens[i];
+  for (int i = lane; i < dm.nsensordata; i += 32) {
+    int k, j;
+    split_copy(i, dm.ns1, K, k, j);
+    if (writes(k)) B.sensordata[(size_t)(e0 + k) * dm.sensor_stride + j] = sens[i];
+  }
   MJB_NOUNROLL
-  for (int i = lane; i < 4 * dm.nprobe; i += 32) g_probe[i] = probe[i];
+  for (int i = lane; i < 4 * dm.nprobe; i += 32) {
+    int k, p1;
+    probe_slot(i >> 2, k, p1);
+    if (writes(k)) B.probe[((size_t)(e0 + k) * dm.np1 + p1) * 4 + (i & 3)] = probe[i];
+  }
   if (mode != MODE_STEP && mode != MODE_RESET) return;
   // ---- epilogue: get_observations (mujoco_parent.py:380-392): sensordata(t) ++ qpos(t+h) ++ qvel(t+h)
   MJB_NOUNROLL
-  for (int a = 0; a < dm.n_agents; a++) {
-    float* oa = B.obs + ((size_t)env * dm.n_agents + a) * dm.obs_stride;
-    int n = dm.obs_adr[a + 1] - dm.obs_adr[a];
+  for (int av = 0; av < dm.n_agents; av++) {
+    int k, a1;
+    split_copy(av, dm.a1, K, k, a1);
+    if (!writes(k)) continue;
+    float* oa = B.obs + ((size_t)(e0 + k) * dm.a1 + a1) * dm.obs_stride;
+    int n = dm.obs_adr[av + 1] - dm.obs_adr[av];
     MJB_NOUNROLL
     for (int i = lane; i < n; i += 32) {
-      int e = CI(obs_index)[dm.obs_adr[a] + i], kind = e >> 24, adr = e & 0xffffff;
+      int e = CI(obs_index)[dm.obs_adr[av] + i], kind = e >> 24, adr = e & 0xffffff;
       oa[i] = kind == 0 ? sens[adr] : (kind == 1 ? qpos[adr] : qvel[adr]);
     }
   }
-  // stage the prefetched rows in shared memory (the contact Jacobian scratch is dead by now)
+  // plugins per real env: its store rows, dynamic actions and step counter are staged in shared memory (the
+  // contact Jacobian scratch is dead by now) so that one lane can run the reference-order programme on them
   int* s_si = (int*)SF(J);
   float* s_sf = SF(J) + MJB_MAX_AGENTS * MJB_STORE_I_COUNT;
   float* s_act = s_sf + MJB_MAX_AGENTS * MJB_STORE_F_COUNT;
   int* s_ts = (int*)(s_act + 64);
-  for (int r = 0; r < 2; r++) {
-    int i = lane + 32 * r;
-    if (i < A_ * dm.store_i32) s_si[i] = pre_si[r];
-    if (i < A_ * dm.act_stride) s_act[i] = pre_act[r];
+  MJB_NOUNROLL
+  for (int k = 0; k < K; k++) {
+    if (!writes(k)) continue;
+    const int env = e0 + k, A1 = dm.a1;
+    int* gsi = B.store_i + (size_t)env * A1 * dm.store_i32;
+    float* gsf = B.store_f + (size_t)env * A1 * dm.store_f32;
+    const float* gact = B.actions + (size_t)env * A1 * dm.act_stride;
+    MJB_SYNC();
+    if (K == 1) {
+      for (int r = 0; r < 2; r++) {
+        int i = lane + 32 * r;
+        if (i < A1 * dm.store_i32) s_si[i] = pre_si[r];
+        if (i < A1 * dm.act_stride) s_act[i] = pre_act[r];
+      }
+      if (lane < A1 * dm.store_f32) s_sf[lane] = pre_sf;
+      if (lane == 0) *s_ts = pre_ts;
+    } else {
+      for (int i = lane; i < A1 * dm.store_i32; i += 32) s_si[i] = gsi[i];
+      for (int i = lane; i < A1 * dm.act_stride; i += 32) s_act[i] = gact[i];
+      if (lane < A1 * dm.store_f32) s_sf[lane] = gsf[lane];
+      if (lane == 0) *s_ts = B.timestep[env];
+    }
+    MJB_SYNC();
+    if (lane == 0) run_plugins(c, B, env, k, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
+    MJB_SYNC();
+    for (int i = lane; i < A1 * dm.store_i32; i += 32) gsi[i] = s_si[i];
+    if (lane < A1 * dm.store_f32) gsf[lane] = s_sf[lane];
+    if (lane == 0) B.timestep[env] = *s_ts;
   }
-  if (lane < A_ * dm.store_f32) s_sf[lane] = pre_sf;
-  if (lane == 0) *s_ts = pre_ts;
-  MJB_SYNC();
-  if (lane == 0) run_plugins(c, B, env, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
-  MJB_SYNC();
-  int* gsi = B.store_i + (size_t)env * A_ * dm.store_i32;
-  float* gsf = B.store_f + (size_t)env * A_ * dm.store_f32;
-  for (int i = lane; i < A_ * dm.store_i32; i += 32) gsi[i] = s_si[i];
-  if (lane < A_ * dm.store_f32) gsf[lane] = s_sf[lane];
-  if (lane == 0) B.timestep[env] = *s_ts;
 }
 
 }  // namespace mjb

@@ -43,7 +43,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // One CTA per SM slot, `warps` environments in flight per CTA; each warp walks the env index space
 // with a grid-wide stride (envs are independent, no inter-warp communication after the staging).
-template <bool PHYS>
+template <bool PHYS, bool PACKED>
 __global__ void __launch_bounds__(512, PHYS ? 1 : 4) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
                       int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env,
                       int lockstep, const int* __restrict__ env_order) {
@@ -73,16 +73,18 @@ __global__ void __launch_bounds__(512, PHYS ? 1 : 4) k_env(const __grid_constant
   //    instruction-cache lines (measured 2x at 65536 envs); costs waiting for the slowest env of the round;
   //  * dynamic: each warp pulls its next env from a grid-wide counter (better balance, poor i-cache reuse).
   const int stride = gridDim.x * warps;
-  const int rounds = (num_envs - blockIdx.x * warps + stride - 1) / stride;
+  const int pack = PACKED ? dm.pack : 1;
+  const int nvirt = (num_envs + pack - 1) / pack;   // virtual envs: `pack` real envs share a warp
+  const int rounds = (nvirt - blockIdx.x * warps + stride - 1) / stride;
   int env = blockIdx.x * warps + warp;
   for (int r = 0;; r++) {
-    if (lockstep ? (r >= rounds) : (env >= num_envs)) break;
+    if (lockstep ? (r >= rounds) : (env >= nvirt)) break;
     if (lockstep == 1 || lockstep == 3) {
-      int busy = num_envs - (blockIdx.x * warps + r * stride);  // env-warps of this CTA with work in this round
+      int busy = nvirt - (blockIdx.x * warps + r * stride);  // env-warps of this CTA with work in this round
       // (a masked reset lets warps skip their env, so intra-step alignment is off for it)
       c.cta_threads = (mask == nullptr ? 32 : 0) * (busy > warps ? warps : (busy < 0 ? 0 : busy));
     }
-    if (env < num_envs) run_env<PHYS>(c, B, (lockstep && env_order) ? env_order[env] : env, mode, skip_frames, mask);
+    if (env < nvirt) run_env<PHYS, PACKED>(c, B, (lockstep && env_order) ? env_order[env] : env, num_envs, mode, skip_frames, mask);
     if (lockstep) {
       if (lockstep != 3) __syncthreads();   // mode 3 aligns inside the step (before the collision phase) instead
       env += stride;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(512, PHYS ? 1 : 4) k_env(const __grid_constant
 }  // namespace mjb
 
 struct mjb_batch {
+  mjb::PackedModel packed;   // K real envs per warp (K = 1: plain)
   mjb::DevImage img;
   mjb::DevImage lite;     // skipFrames = 0 only: state-rows-only scratch layout for the step kernel
   bool has_lite = false;
@@ -148,12 +151,13 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
   (void)first;
   if (mode == mjb::MODE_STEP && b->has_lite) {
     // no physics in the step: many small envs per SM, rounds aligned the same way
-    mjb::k_env<false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, b->stream>>>(b->lite.dm, b->d_image, b->B, b->num_envs, mode,
+    mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, b->stream>>>(b->lite.dm, b->d_image, b->B, b->num_envs, mode,
                                                                                       skip_frames, mask, counter, 2, nullptr);
   } else {
-    mjb::k_env<true><<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode,
-                                                                             skip_frames, mask, counter, b->lockstep,
-                                                                             b->lockstep ? b->env_order : nullptr);
+    auto kern = b->img.dm.pack > 1 ? mjb::k_env<true, true> : mjb::k_env<true, false>;
+    kern<<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode, skip_frames, mask,
+                                                                counter, b->lockstep,
+                                                                (b->lockstep && b->img.dm.pack == 1) ? b->env_order : nullptr);
   }
   CUDA_TRY(cudaGetLastError());
   if (b->timing) {
@@ -196,8 +200,10 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
   }
   mjb_batch* b = new mjb_batch();
   try {
-    mjb::ModelView mv(m->host.blob.data());
-    mjb::build_dev_model(mv, *spec, b->img);
+    const int K = mjb::choose_pack(m->host, *spec, num_envs);
+    mjb::make_packed(m->host, *spec, K, b->packed);
+    mjb::ModelView mv(K > 1 ? b->packed.rep.blob.data() : m->host.blob.data());
+    mjb::build_dev_model(mv, b->packed.vspec, b->img, false, K);
   } catch (const std::exception& e) {
     mjb::set_error(e.what());
     delete b;
@@ -228,14 +234,16 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
   if (warps < 1) { mjb::set_error("model needs more shared memory per environment than one SM has"); return fail(MJB_ERR_LIMIT); }
   // even out the rounds: the fewest warps per CTA that keeps the same number of passes over the envs
   int sms = prop.multiProcessorCount * ctas;
-  int rounds = (num_envs + sms * warps - 1) / (sms * warps);
-  int even = (num_envs + sms * rounds - 1) / (sms * rounds);
+  const int nvirt = (num_envs + dm.pack - 1) / dm.pack;
+  int rounds = (nvirt + sms * warps - 1) / (sms * warps);
+  int even = (nvirt + sms * rounds - 1) / (sms * rounds);
   if (even < warps) warps = even < 1 ? 1 : even;
   b->warps = warps;
-  b->grid = (num_envs + warps - 1) / warps;
+  b->grid = (nvirt + warps - 1) / warps;
   if (b->grid > sms) b->grid = sms;
   b->smem_bytes = fixed + per_env * warps;
-  if (cudaFuncSetAttribute(mjb::k_env<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(mjb::k_env<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(mjb::k_env<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes) != cudaSuccess) {
     mjb::set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(cudaGetLastError()));
     return fail(MJB_ERR_CUDA);
   }
@@ -248,8 +256,8 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     b->lite_warps = 16;
     b->lite_smem = fixed + lite_env * b->lite_warps;
     int per_sm = 1;
-    if (cudaFuncSetAttribute(mjb::k_env<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lite_smem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mjb::k_env<false>, b->lite_warps * 32, b->lite_smem) != cudaSuccess || per_sm < 1) {
+    if (cudaFuncSetAttribute(mjb::k_env<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lite_smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mjb::k_env<false, false>, b->lite_warps * 32, b->lite_smem) != cudaSuccess || per_sm < 1) {
       mjb::set_error("lite step kernel configuration failed");
       return fail(MJB_ERR_CUDA);
     }

@@ -30,14 +30,30 @@ int emu_layout(const void* blob, const mjb_env_spec* spec, int num_envs, mjb_lay
 int emu_run(const void* blob, const mjb_env_spec* spec, int num_envs, const mjb_buffers* B, int mode, int skip_frames,
             const uint8_t* mask, int reverse) {
   try {
-    mjb::ModelView mv(blob);
+    // the emulator receives the blob only: rebuild the host model fields from it to be able to replicate
+    mjb::HostModel host;
+    {
+      const mjb_blob_header* h = (const mjb_blob_header*)blob;
+      const mjb_blob_field* f = (const mjb_blob_field*)((const char*)blob + sizeof(mjb_blob_header));
+      for (int i = 0; i < h->nfields; i++) {
+        std::string name(f[i].name);
+        if (f[i].dtype == MJB_DTYPE_I32) host.I(name).assign((const int32_t*)((const char*)blob + f[i].offset), (const int32_t*)((const char*)blob + f[i].offset) + f[i].count);
+        else host.F(name).assign((const double*)((const char*)blob + f[i].offset), (const double*)((const char*)blob + f[i].offset) + f[i].count);
+      }
+      host.pack();
+    }
+    const int K = mjb::choose_pack(host, *spec, num_envs);
+    mjb::PackedModel packed;
+    mjb::make_packed(host, *spec, K, packed);
+    mjb::ModelView mv(K > 1 ? (const void*)packed.rep.blob.data() : blob);
     mjb::DevImage img;
-    mjb::build_dev_model(mv, *spec, img);
+    mjb::build_dev_model(mv, packed.vspec, img, false, K);
     std::vector<float> scratch(img.dm.env_words + 64, 0.f), probe(4 * img.dm.nprobe + 4, 0.f);
-    for (int env = 0; env < num_envs; env++) {
+    const int nvirt = (num_envs + K - 1) / K;
+    for (int env = 0; env < nvirt; env++) {
       simt::run_warp([&]() {
         mjb::Ctx c{&img.dm, img.words.data(), scratch.data(), simt::lane(), probe.data(), 0, 0};
-        mjb::run_env<true>(c, *B, env, mode, skip_frames, mask);
+        mjb::run_env<true, true>(c, *B, env, num_envs, mode, skip_frames, mask);
       }, reverse != 0);
     }
     return 0;
