@@ -106,3 +106,42 @@ def test_full_step_with_plugins_against_host_loop():
         assert eb.timestep[0] == env.timestep
         tgt = [targets.index(env.data_store[a]["current_target"]) + 1 for a in agents]
         assert list(eb.store_i[0, :, L.STORE_I["current_target"]]) == tgt
+
+
+def test_packed_envs_ragged_count_and_masked_reset():
+    """Env packing (csrc/replicate.h): an Ant has 14 dofs, so two real envs share a warp.  Five envs (the last
+    virtual env holds a single copy), ant reward in the epilogue, then a masked reset of envs 1 and 4 only."""
+    model, tables, agents, fj = load_scene("1A")
+    spec, keep = make_spec(model, tables, agents, fj, skip_frames=2, rewards=[(L.REW_ANT, 0.0)], max_steps=4)
+    N = 5
+    eb = E.EmuBatch(model.blob, spec, N, keep)
+
+    def resolve(name):
+        b = model.name2id(L.OBJ_BODY, name)
+        return (1, b) if b >= 0 else (5, model.name2id(L.OBJ_GEOM, name))
+    envs = [H.OracleEnv(model, tables, agents, skip_frames=2, max_steps=4, reward_functions=[H.ant_reward], resolve=resolve)
+            for _ in range(N)]
+    eb.run(E.MODE_RESET)
+    for e in envs:
+        e.reset({"torso": np.zeros(8)})
+    rng = np.random.default_rng(17)
+    for t in range(6):
+        act = rng.uniform(-1, 1, (N, 1, 8))
+        for e, env in enumerate(envs):
+            eb.qpos[e, :15], eb.qvel[e, :14], eb.ctrl[e, :8] = env.sim.qpos, env.sim.qvel, env.sim.ctrl
+        eb.actions[:, :, :8] = act
+        eb.run(E.MODE_STEP, 2)
+        for e, env in enumerate(envs):
+            o, r, term, trunc, _ = env.step({"torso": act[e, 0]})
+            assert rel_err(eb.obs[e, 0, :29], o["torso"]) < 3 * RTOL, (t, e)
+            assert abs(eb.reward[e, 0] - r["torso"]) < 2e-2 * max(1.0, abs(r["torso"])), (t, e)
+            assert bool(eb.trunc[e, 0]) == trunc["torso"] and eb.timestep[e] == env.timestep
+    q_before = eb.qpos.copy()
+    mask = np.array([0, 1, 0, 0, 1], np.uint8)
+    eb.run(E.MODE_RESET, mask=mask)
+    for e in range(N):
+        if mask[e]:
+            assert np.allclose(eb.qpos[e, :15], model.fields["qpos0"], atol=1e-6) and eb.timestep[e] == 0
+            assert not eb.store_i[e, :, :5].any()
+        else:
+            assert np.array_equal(eb.qpos[e], q_before[e]) and eb.timestep[e] == 6
