@@ -122,7 +122,7 @@ struct DevPlugin {
 struct DevModel {
   // sizes
   int nq, nv, nu, nmb, njnt, nlim, ngeom, ngdyn, nsite, nsensor, nsensordata, npair, nclass, nlevel, nprobe;
-  int maxcon, maxcand, maxefc, ldm, ldj, maxtree;
+  int maxcon, maxcand, maxefc, ldj, maxtree;
   // packing: `pack` real envs per warp (see replicate.h); the *1 sizes are those of ONE real env
   int pack, a1, t1, nq1, nv1, nu1, ns1, np1, ngeom1, maxcon1;
   int integrator, has_damping, need_acc_sensors;

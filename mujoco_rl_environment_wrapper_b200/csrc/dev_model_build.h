@@ -86,7 +86,7 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   dm.nsite = m.nsite; dm.nsensor = m.nsensor; dm.nsensordata = m.nsensordata; dm.npair = m.npair;
   dm.nlevel = nlevel; dm.integrator = m.integrator; dm.timestep = (float)m.timestep;
   for (int i = 0; i < 3; i++) dm.gravity[i] = (float)m.gravity[i];
-  dm.ldm = m.nv | 1; dm.ldj = m.nv | 1;  // ldj is narrowed below to the widest contact dof mask
+  dm.ldj = m.nv | 1;  // narrowed below to the widest contact dof mask
   dm.solver_iterations = spec.solver_iterations > 0 ? spec.solver_iterations : env_int("MJB_SOLVER_ITERS", 24);
   dm.ls_iterations = spec.ls_iterations > 0 ? spec.ls_iterations : env_int("MJB_LS_ITERS", 12);
   {

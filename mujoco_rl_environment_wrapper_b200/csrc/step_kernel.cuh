@@ -96,7 +96,6 @@ struct Ctx {
 // packed lower triangle: element (i, j), j <= i.  Lane i reading (i, k) is bank-conflict free for
 // i < 32 (triangular numbers are distinct mod 32).
 MJB_DEV int tri(int i, int j) { return ((i * (i + 1)) >> 1) + j; }
-MJB_DEV int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
 
 // spatial helpers: motion [w; v], force [n; f], inertia {m, h(3), I(6: xx yy zz xy xz yz)} about o
 MJB_DEV void inertia_mul(const float* I, f3 w, f3 v, f3& n, f3& f) {
@@ -218,7 +217,7 @@ MJB_DEV void fk(const Ctx& c) {
   MJB_SYNC();
 }
 
-// composite rigid body inertias and the joint-space inertia matrix (dense, ld = dm.ldm)
+// composite rigid body inertias and the joint-space inertia matrix (packed lower triangle)
 MJB_DEV void crb_mass(const Ctx& c) {
   const DevModel& dm = *c.dm;
   const int* level_adr = CI(level_adr);
