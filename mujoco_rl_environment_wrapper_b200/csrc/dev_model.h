@@ -83,6 +83,7 @@ namespace mjb {
   X(probe_const)    /* f32 [nprobe*3]  value for constant (static) probes                        */ \
   X(act_index)      /* int [n_agents*n_phys_act]                                                 */ \
   X(obs_index)      /* int [sum obs]   (kind << 24) | address                                    */ \
+  X(tri_lut)        /* u32 [136]       pair p = r (r + 1) / 2 + c  ->  r | c << 8   (r >= c, r < 16)       */ \
   X(qpos0)          /* f32 [nq]                                                                  */
 
 enum ImageField {
@@ -146,7 +147,8 @@ struct DevModel {
 };
 
 // contact record layout inside SF_con (16 words per contact)
-enum { CON_DIST = 0, CON_POS = 1, CON_FRAME = 4, CON_PAIR = 13, CON_MU = 14, CON_MASK = 15, CON_STRIDE = 16 };
+// (CON_DOFS: the dofs of the contact's mask as up to 16 packed bytes, ascending)
+enum { CON_DIST = 0, CON_POS = 1, CON_FRAME = 4, CON_PAIR = 13, CON_MU = 14, CON_MASK = 15, CON_DOFS = 16, CON_STRIDE = 20 };
 enum { LIM_LO = 0, LIM_HI, LIM_MARGIN, LIM_K, LIM_B, LIM_INVW, LIM_SOLIMP, LIM_STRIDE = 12 };
 enum { PC_MARGIN = 0, PC_INCMARGIN, PC_MU, PC_K, PC_B, PC_SOLIMP, PC_CONDIM = 10, PC_STRIDE = 12 };
 enum { DOF_AXIS = 0, DOF_FREE_TRANS = 1, DOF_FREE_ROT = 2 };

@@ -359,6 +359,8 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
     w.i(e);
   }
   if (spec.obs_adr[spec.n_agents] == 0) w.i(0);
+  w.begin(IF_tri_lut);
+  for (int r = 0; r < 16; r++) for (int cc = 0; cc <= r; cc++) w.u((uint32_t)r | ((uint32_t)cc << 8));
   w.begin(IF_qpos0); for (int i = 0; i < m.nq; i++) w.f(m.qpos0[i]);
   while (W.size() % 4) W.push_back(0);
   dm.image_words = (int)W.size();

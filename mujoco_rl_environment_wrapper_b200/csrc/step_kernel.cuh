@@ -664,7 +664,17 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
     float* r = con + CON_STRIDE * k;
     uint32_t pk = pairs[((const int*)r)[CON_PAIR]];
     int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
-    ((uint32_t*)r)[CON_MASK] = (b1 >= 0 ? CU(mb_dofmask)[2 * b1] : 0u) ^ (b2 >= 0 ? CU(mb_dofmask)[2 * b2] : 0u);
+    uint32_t mask = (b1 >= 0 ? CU(mb_dofmask)[2 * b1] : 0u) ^ (b2 >= 0 ? CU(mb_dofmask)[2 * b2] : 0u);
+    ((uint32_t*)r)[CON_MASK] = mask;
+    uint32_t words[4] = {0u, 0u, 0u, 0u};
+    int m = 0;
+    MJB_NOUNROLL
+    while (mask && m < 16) {
+      words[m >> 2] |= (uint32_t)(MJB_FFS(mask) - 1) << (8 * (m & 3));
+      mask &= mask - 1;
+      m++;
+    }
+    for (int i = 0; i < 4; i++) ((uint32_t*)r)[CON_DOFS + i] = words[i];
   }
   MJB_SYNC();
   MJB_NOUNROLL
@@ -1003,24 +1013,19 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       if (cnn == 0.f) continue;  // warp-uniform
       if (b1 >= 0 && b2 >= 0 && CI(mb_root)[b1] != CI(mb_root)[b2]) coupled = true;
       float cn1 = mu * (w0 - w1), c11 = mu * mu * (w0 + w1), cn2 = mu * (w2 - w3), c22 = mu * mu * (w2 + w3);
-      bool mine = lane < nv && ((mask >> lane) & 1u);
-      float jn = 0.f, j1 = 0.f, j2 = 0.f;
-      if (mine) {
-        int idx = MJB_POPC(mask & ((1u << lane) - 1u));
-        jn = J[(3 * k) * dm.ldj + idx]; j1 = J[(3 * k + 1) * dm.ldj + idx]; j2 = J[(3 * k + 2) * dm.ldj + idx];
-      }
-      // row i (lane) x column j (set bits of mask, j <= i)
-      float ri_n = cnn * jn + cn1 * j1 + cn2 * j2, ri_1 = cn1 * jn + c11 * j1, ri_2 = cn2 * jn + c22 * j2;
-      uint32_t mm = mask;
-      int m = 0;
+      // lanes = (row, column) pairs of the contact's dofs: H(di, dj) += sum_edges w_e J_e[di] J_e[dj]
+      const int nb = MJB_POPC(mask), npairs = (nb * (nb + 1)) >> 1;
+      const uint32_t* dofs = (const uint32_t*)(con + CON_STRIDE * k) + CON_DOFS;
+      const float *Jn = J + (3 * k) * dm.ldj, *J1 = Jn + dm.ldj, *J2 = J1 + dm.ldj;
       MJB_NOUNROLL
-      while (mm) {
-        int j = MJB_FFS(mm) - 1;
-        mm &= mm - 1;
-        if (mine && j <= lane)
-          H[tri(lane, j)] += ri_n * J[(3 * k) * dm.ldj + m] + ri_1 * J[(3 * k + 1) * dm.ldj + m] + ri_2 * J[(3 * k + 2) * dm.ldj + m];
-        m++;
+      for (int p = lane; p < npairs; p += 32) {
+        uint32_t rc = CU(tri_lut)[p];
+        int mi = rc & 0xff, mj = rc >> 8;
+        int di = (dofs[mi >> 2] >> (8 * (mi & 3))) & 0xff, dj = (dofs[mj >> 2] >> (8 * (mj & 3))) & 0xff;
+        float ni = Jn[mi], ai = J1[mi], bi = J2[mi], nj = Jn[mj], aj = J1[mj], bj = J2[mj];
+        H[tri(di, dj)] += ni * (cnn * nj + cn1 * aj + cn2 * bj) + ai * (cn1 * nj + c11 * aj) + bi * (cn2 * nj + c22 * bj);
       }
+      MJB_SYNC();  // the next contact may touch the same entries from other lanes
     }
     MJB_SYNC();
     // factor per tree block unless a contact couples trees (then one block over all dofs)
