@@ -78,6 +78,9 @@ namespace mjb {
   X(sensor_cutoff)  /* f32 [nsensor]                                                             */ \
   X(act_dof)        /* int [nu]                                                                  */ \
   X(act_param)      /* f32 [nu*4]      gear, ctrllimited, lo, hi                                 */ \
+  X(dof_actadr)     /* int [nv]        actuators acting on a dof: range in act_list              */ \
+  X(dof_actnum)     /* int [nv]                                                                  */ \
+  X(act_list)       /* int [nu]        actuator ids grouped by dof                               */ \
   X(probe_kind)     /* int [nprobe]    0 body xipos (kernel body), 1 geom xpos, 2 constant       */ \
   X(probe_id)       /* int [nprobe]                                                              */ \
   X(probe_const)    /* f32 [nprobe*3]  value for constant (static) probes                        */ \

@@ -303,6 +303,17 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
     w.f(m.actuator_gear[u]); w.f(m.actuator_ctrllimited[u]); w.f(m.actuator_ctrlrange[2 * u]); w.f(m.actuator_ctrlrange[2 * u + 1]);
   }
   if (!m.nu) for (int i = 0; i < 4; i++) w.f(0);
+  {
+    std::vector<int> adr(m.nv, 0), num(m.nv, 0), list;
+    for (int d = 0; d < m.nv; d++) {
+      adr[d] = (int)list.size();
+      for (int u = 0; u < m.nu; u++)
+        if (m.jnt_dofadr[m.actuator_trnid[u]] == d) { list.push_back(u); num[d]++; }
+    }
+    w.begin(IF_dof_actadr); for (int v : adr) w.i(v);
+    w.begin(IF_dof_actnum); for (int v : num) w.i(v);
+    w.begin(IF_act_list); for (int v : list) w.i(v); if (list.empty()) w.i(0);
+  }
 
   // ---- env spec: agents, probes, plugins
   if (spec.n_agents < 0 || spec.n_agents > MJB_MAX_AGENTS) throw std::runtime_error("n_agents out of range");

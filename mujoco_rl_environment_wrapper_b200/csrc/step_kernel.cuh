@@ -330,13 +330,13 @@ MJB_DEV void rne_pass(const Ctx& c, bool with_acc) {
     float bias = dot(ld3(cdof + 6 * d), ld3(cfrc + 10 * b)) + dot(ld3(cdof + 6 * d + 3), ld3(cfrc + 10 * b + 3));
     float f = -CF(dof_damping)[d] * qvel[d] - bias;
     MJB_NOUNROLL
-    for (int u = 0; u < dm.nu; u++)
-      if (CI(act_dof)[u] == d) {
-        const float* ap = CF(act_param) + 4 * u;
-        float cv = ctrl[u];
-        if (ap[1] != 0.f) cv = fminf(ap[3], fmaxf(ap[2], cv));
-        f += ap[0] * cv;
-      }
+    for (int k = CI(dof_actadr)[d]; k < CI(dof_actadr)[d] + CI(dof_actnum)[d]; k++) {
+      int u = CI(act_list)[k];
+      const float* ap = CF(act_param) + 4 * u;
+      float cv = ctrl[u];
+      if (ap[1] != 0.f) cv = fminf(ap[3], fmaxf(ap[2], cv));
+      f += ap[0] * cv;
+    }
     qfrc[d] = f;
   }
   MJB_SYNC();
@@ -1033,9 +1033,34 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     float s = factor_solve(H, H, lane, h0, h1, hb, 0.f, lane < nv ? -g : 0.f, nv);
     if (lane < nv) sv[lane] = s;
     MJB_SYNC();
-    float mv = 0.f;
-    if (lane < nv) { mv = matvec_row(M, sv, lane, t0, t1); Mv[lane] = mv; }
     rows_mul(c, ncon, sv, jv, nullptr);
+    // M s without a matrix product: H s = -g and H = M + J' W J  =>  M s = -g - J' (W (J s)), W = active D
+    float mv = 0.f;
+    if (lane < nv) {
+      mv = -g;
+      MJB_NOUNROLL
+      for (int k = 0; k < ncon; k++) {
+        uint32_t mask = ((const uint32_t*)(con + CON_STRIDE * k))[CON_MASK];
+        if (!((mask >> lane) & 1u)) continue;
+        float mu = con[CON_STRIDE * k + CON_MU];
+        float u0 = jar[base + 4 * k] < 0 ? D[base + 4 * k] * jv[base + 4 * k] : 0.f;
+        float u1 = jar[base + 4 * k + 1] < 0 ? D[base + 4 * k + 1] * jv[base + 4 * k + 1] : 0.f;
+        float u2 = jar[base + 4 * k + 2] < 0 ? D[base + 4 * k + 2] * jv[base + 4 * k + 2] : 0.f;
+        float u3 = jar[base + 4 * k + 3] < 0 ? D[base + 4 * k + 3] * jv[base + 4 * k + 3] : 0.f;
+        int idx = MJB_POPC(mask & ((1u << lane) - 1u));
+        mv -= J[(3 * k) * dm.ldj + idx] * (u0 + u1 + u2 + u3) + J[(3 * k + 1) * dm.ldj + idx] * mu * (u0 - u1) +
+              J[(3 * k + 2) * dm.ldj + idx] * mu * (u2 - u3);
+      }
+      Mv[lane] = mv;
+    }
+    MJB_SYNC();
+    MJB_NOUNROLL
+    for (int k = lane; k < dm.nlim; k += 32) {
+      float ulo = jar[2 * k] < 0 ? D[2 * k] * jv[2 * k] : 0.f, uhi = jar[2 * k + 1] < 0 ? D[2 * k + 1] * jv[2 * k + 1] : 0.f;
+      Mv[CI(lim_dof)[k]] -= ulo - uhi;
+    }
+    MJB_SYNC();
+    mv = lane < nv ? Mv[lane] : 0.f;
     float p1 = wsum(lane < nv ? s * (Ma[lane] - qfrc[lane]) : 0.f);
     float p2 = wsum(lane < nv ? s * mv : 0.f);
     // exact line search on the convex piecewise-quadratic phi(alpha): safeguarded Newton on phi'
