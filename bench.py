@@ -60,7 +60,7 @@ def _cpu_env(seed):
         from mujoco_rl_environment_wrapper_b200 import _lib as L
         from mujoco_rl_environment_wrapper_b200.tables import Tables
         from oracle import host_loop as H
-        text = open(os.path.join(LEVELS, "MultiAgentModel.xml")).read()
+        text = open(os.path.join(LEVELS, "two_ants.xml")).read()
         model = L.Model(text)
         agents = ["sender", "receiver"]
         tables = Tables(text, model, agents, False)
@@ -184,7 +184,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     N = ENVS_PER_GPU
-    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "two_ants.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
                     "agents": ["sender", "receiver"], "skipFrames": 1, "maxSteps": 1024, "num_envs": N,
                     "seed": 1234 + 1000 * rank, "device": dev, "environmentDynamics": [P.Language],
                     "rewardFunctions": [P.tag_distance_reward], "doneFunctions": [P.distance_done]})

@@ -12,14 +12,14 @@ LEVELS = os.path.join(ROOT, "tests", "levels")
 
 SCENES = {
     # name: (xml, agents, free_joint)
-    "2A": ("MultiAgentModel.xml", ["sender", "receiver"], False),
-    "1A": ("Ant.xml", ["torso"], False),
-    "C1": ("SingleAgentModel.xml", ["sender"], False),
-    "3S": ("MultiAgentModel3Sensors.xml", ["sender", "receiver"], True),
-    "S1": ("sensor_levels/Model1.xml", ["receiver"], True),
-    "S2": ("sensor_levels/Model2.xml", ["receiver"], True),
-    "S3": ("sensor_levels/Model3.xml", ["receiver"], True),
-    "S4": ("sensor_levels/Model4.xml", ["receiver"], True),
+    "2A": ("two_ants.xml", ["sender", "receiver"], False),
+    "1A": ("ant_rk4.xml", ["torso"], False),
+    "C1": ("one_ant_arena.xml", ["sender"], False),
+    "3S": ("two_ants_touch_acc.xml", ["sender", "receiver"], True),
+    "S1": ("box_touch.xml", ["receiver"], True),
+    "S2": ("box_accelerometer.xml", ["receiver"], True),
+    "S3": ("box_rangefinder.xml", ["receiver"], True),
+    "S4": ("box_framexaxis.xml", ["receiver"], True),
 }
 
 

@@ -210,15 +210,15 @@ def main():
     install_stubs()
     sys.path.insert(0, REF)
     from MuJoCo_Gym.mujoco_rl import MuJoCoRL  # the real reference class
-    levels = os.path.join(ROOT, "tests", "levels")
+    levels = REF   # the reference's own level files, fed to the reference's own host code
     out_tables = {}
-    for name, xml, agents, fj in [("2A", "MultiAgentModel.xml", ["sender", "receiver"], False),
-                                   ("2A_free", "MultiAgentModel.xml", ["sender", "receiver"], True),
-                                   ("3S_free", "MultiAgentModel3Sensors.xml", ["sender", "receiver"], True),
-                                   ("1A", "Ant.xml", ["torso"], False),
-                                   ("C1", "SingleAgentModel.xml", ["sender"], False),
-                                   ("S1_free", "sensor_levels/Model1.xml", ["receiver"], True),
-                                   ("S3_free", "sensor_levels/Model3.xml", ["receiver"], True)]:
+    for name, xml, agents, fj in [("2A", "benchmarking/levels/MultiAgentModel.xml", ["sender", "receiver"], False),
+                                   ("2A_free", "benchmarking/levels/MultiAgentModel.xml", ["sender", "receiver"], True),
+                                   ("3S_free", "benchmarking/levels/MultiAgentModel3Sensors.xml", ["sender", "receiver"], True),
+                                   ("1A", "benchmarking/levels/Ant.xml", ["torso"], False),
+                                   ("C1", "benchmarking/levels/SingleAgentModel.xml", ["sender"], False),
+                                   ("S1_free", "Testing/sensor_levels/Model1.xml", ["receiver"], True),
+                                   ("S3_free", "Testing/sensor_levels/Model3.xml", ["receiver"], True)]:
         cfg = {"xmlPath": os.path.join(levels, xml), "agents": agents, "freeJoint": fj, "skipFrames": 1}
         if name in ("1A", "S1_free", "S3_free") and not fj:
             pass
@@ -242,7 +242,7 @@ def main():
     draw_log = []
     Language, reward_function, done_function = make_plugins(draw_log)
     random.seed(7)
-    cfg = {"xmlPath": os.path.join(levels, "MultiAgentModel.xml"), "infoJson": os.path.join(levels, "info_2A.json"),
+    cfg = {"xmlPath": os.path.join(levels, "benchmarking/levels/MultiAgentModel.xml"), "infoJson": os.path.join(ROOT, "tests", "levels", "info_2A.json"),
            "agents": ["sender", "receiver"], "freeJoint": False, "skipFrames": 1, "maxSteps": 5,
            "environmentDynamics": [Language], "rewardFunctions": [reward_function], "doneFunctions": [done_function]}
     env = MuJoCoRL(cfg)

@@ -100,7 +100,7 @@ def test_full_step_C2_flags_bit_exact():
     from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
     from mujoco_rl_environment_wrapper_b200 import plugins as P
     N, seed, max_steps = 64, 4321, 7
-    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "two_ants.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
                     "agents": ["sender", "receiver"], "skipFrames": 1, "maxSteps": max_steps, "num_envs": N, "seed": seed,
                     "environmentDynamics": [P.Language], "rewardFunctions": [P.tag_distance_reward],
                     "doneFunctions": [P.distance_done]})
@@ -189,7 +189,7 @@ def test_literal_skipframes0_freejoint():
     from mujoco_rl_environment_wrapper_b200.tables import Tables
     import os
     from common import LEVELS
-    text = open(os.path.join(LEVELS, "Ant.xml")).read()
+    text = open(os.path.join(LEVELS, "ant_rk4.xml")).read()
     tables = Tables(text, model, agents, True)
     spec, keep = make_spec(model, tables, agents, True, skip_frames=0, rewards=[(L.REW_ANT, 0.0)])
     b = _batch(model, spec, 128, keep)
@@ -236,7 +236,7 @@ def test_pick_up_dynamic_C5():
     from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
     from mujoco_rl_environment_wrapper_b200 import plugins as P
     N, seed = 32, 77
-    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "two_ants.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
                     "agents": ["sender", "receiver"], "num_envs": N, "seed": seed, "environmentDynamics": [P.PickUpDynamic]})
     assert env.observation_space("sender").shape == (63,) and env.action_space("sender").shape == (8,)
     mirrors = [_mirror_env(env, e, seed, [H.PickUp], [], [], ["choice_1", "choice_2"]) for e in range(N)]
@@ -272,7 +272,7 @@ def test_ant_reward_rk4_C3_and_skipframes():
     from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
     from mujoco_rl_environment_wrapper_b200 import plugins as P
     N = 16
-    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "Ant.xml"), "agents": ["torso"], "num_envs": N, "skipFrames": 5,
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "ant_rk4.xml"), "agents": ["torso"], "num_envs": N, "skipFrames": 5,
                     "rewardFunctions": [P.ant_reward_function], "maxSteps": 3})
     mirrors = [_mirror_env(env, e, 0, [], [H.ant_reward], [], [], skip_frames=5, max_steps=3) for e in range(N)]
     env.reset()
@@ -329,7 +329,7 @@ def test_single_env_squeezes_to_reference_shapes_and_wrappers():
     from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
     from mujoco_rl_environment_wrapper_b200.wrappers import GymnasiumWrapper, GymWrapper
     from mujoco_rl_environment_wrapper_b200 import plugins as P
-    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "Ant.xml"), "agents": ["torso"], "maxSteps": 2,
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "ant_rk4.xml"), "agents": ["torso"], "maxSteps": 2,
                     "rewardFunctions": [P.ant_reward_function]})
     obs, infos = env.reset()
     assert isinstance(obs["torso"], np.ndarray) and obs["torso"].dtype == np.float64 and obs["torso"].shape == (29,)
@@ -346,7 +346,7 @@ def test_single_env_squeezes_to_reference_shapes_and_wrappers():
     o, r, done, info = GymWrapper(env, "torso").step(np.zeros(8, np.float32))
     assert done is False
     with pytest.raises(Exception, match="too many agents"):
-        two = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "agents": ["sender", "receiver"]})
+        two = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "two_ants.xml"), "agents": ["sender", "receiver"]})
         GymnasiumWrapper(two, "sender")
 
 
@@ -377,7 +377,7 @@ def test_user_plugins_run_as_batched_torch_code():
         return torch.zeros(env.num_envs, dtype=torch.bool, device=env.device)
 
     N = 8
-    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "agents": ["sender", "receiver"], "num_envs": N,
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "two_ants.xml"), "agents": ["sender", "receiver"], "num_envs": N,
                     "environmentDynamics": [P.Language, Echo], "rewardFunctions": [height_reward], "doneFunctions": [never_done]})
     assert env.action_routing["dynamic"] == {"Language": [8, 9], "Echo": [9, 11]}
     assert env.observation_space("sender").shape == (62,) and env.action_space("sender").shape == (11,)
@@ -401,7 +401,7 @@ def test_queries_distance_collision_get_data_filter_by_tag():
     from common import LEVELS
     from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
     N = 16
-    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "MultiAgentModel.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
+    env = MuJoCoRL({"xmlPath": os.path.join(LEVELS, "two_ants.xml"), "infoJson": os.path.join(LEVELS, "info_2A.json"),
                     "agents": ["sender", "receiver"], "num_envs": N})
     env.reset()
     tg = env.filter_by_tag("target")

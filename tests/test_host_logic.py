@@ -16,12 +16,12 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def _tables_for(name):
     xml, agents, fj = {
-        "2A": ("MultiAgentModel.xml", ["sender", "receiver"], False),
-        "2A_free": ("MultiAgentModel.xml", ["sender", "receiver"], True),
-        "3S_free": ("MultiAgentModel3Sensors.xml", ["sender", "receiver"], True),
-        "1A": ("Ant.xml", ["torso"], False), "C1": ("SingleAgentModel.xml", ["sender"], False),
-        "S1_free": ("sensor_levels/Model1.xml", ["receiver"], True),
-        "S3_free": ("sensor_levels/Model3.xml", ["receiver"], True)}[name]
+        "2A": ("two_ants.xml", ["sender", "receiver"], False),
+        "2A_free": ("two_ants.xml", ["sender", "receiver"], True),
+        "3S_free": ("two_ants_touch_acc.xml", ["sender", "receiver"], True),
+        "1A": ("ant_rk4.xml", ["torso"], False), "C1": ("one_ant_arena.xml", ["sender"], False),
+        "S1_free": ("box_touch.xml", ["receiver"], True),
+        "S3_free": ("box_rangefinder.xml", ["receiver"], True)}[name]
     text = open(os.path.join(LEVELS, xml)).read()
     model = L.Model(text)
     return model, Tables(text, model, agents, fj), agents

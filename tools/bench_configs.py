@@ -25,16 +25,16 @@ LV = os.path.join(ROOT, "tests", "levels")
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 CONFIGS = [
-    ("C1", dict(xmlPath="SingleAgentModel.xml", agents=["sender"]), 16384),
-    ("C2", dict(xmlPath="MultiAgentModel.xml", infoJson="info_2A.json", agents=["sender", "receiver"], environmentDynamics=[P.Language],
+    ("C1", dict(xmlPath="one_ant_arena.xml", agents=["sender"]), 16384),
+    ("C2", dict(xmlPath="two_ants.xml", infoJson="info_2A.json", agents=["sender", "receiver"], environmentDynamics=[P.Language],
                 rewardFunctions=[P.tag_distance_reward], doneFunctions=[P.distance_done]), 4096),
-    ("C2", dict(xmlPath="MultiAgentModel.xml", infoJson="info_2A.json", agents=["sender", "receiver"], environmentDynamics=[P.Language],
+    ("C2", dict(xmlPath="two_ants.xml", infoJson="info_2A.json", agents=["sender", "receiver"], environmentDynamics=[P.Language],
                 rewardFunctions=[P.tag_distance_reward], doneFunctions=[P.distance_done]), 65536),
-    ("C3-literal", dict(xmlPath="Ant.xml", agents=["torso"], freeJoint=True, skipFrames=0, rewardFunctions=[P.ant_reward_function]), 65536),
-    ("C3-physics-skip1", dict(xmlPath="Ant.xml", agents=["torso"], skipFrames=1, rewardFunctions=[P.ant_reward_function]), 65536),
-    ("C3-physics-skip5", dict(xmlPath="Ant.xml", agents=["torso"], skipFrames=5, rewardFunctions=[P.ant_reward_function]), 65536),
-    ("C4", dict(xmlPath="MultiAgentModel3Sensors.xml", agents=["sender", "receiver"], freeJoint=True, skipFrames=5), 16384),
-    ("C5", dict(xmlPath="MultiAgentModel.xml", infoJson="info_2A.json", agents=["sender", "receiver"], environmentDynamics=[P.PickUpDynamic]), 32768),
+    ("C3-literal", dict(xmlPath="ant_rk4.xml", agents=["torso"], freeJoint=True, skipFrames=0, rewardFunctions=[P.ant_reward_function]), 65536),
+    ("C3-physics-skip1", dict(xmlPath="ant_rk4.xml", agents=["torso"], skipFrames=1, rewardFunctions=[P.ant_reward_function]), 65536),
+    ("C3-physics-skip5", dict(xmlPath="ant_rk4.xml", agents=["torso"], skipFrames=5, rewardFunctions=[P.ant_reward_function]), 65536),
+    ("C4", dict(xmlPath="two_ants_touch_acc.xml", agents=["sender", "receiver"], freeJoint=True, skipFrames=5), 16384),
+    ("C5", dict(xmlPath="two_ants.xml", infoJson="info_2A.json", agents=["sender", "receiver"], environmentDynamics=[P.PickUpDynamic]), 32768),
 ]
 
 

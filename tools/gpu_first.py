@@ -9,7 +9,7 @@ from oracle import OracleSim
 import emu_harness as E
 
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-xml = os.path.join(root, "tests", "levels", "MultiAgentModel.xml")
+xml = os.path.join(root, "tests", "levels", "two_ants.xml")
 model = L.Model.from_xml_path(xml)
 spec, keep = E.simple_spec(model, [model.name2id(L.OBJ_BODY, 'sender'), model.name2id(L.OBJ_BODY, 'receiver')],
                            [2, 3, 4, 5, 6, 7, 0, 1, 10, 11, 12, 13, 14, 15, 8, 9], 8, obs_sensors=[[0], [1]])
