@@ -368,6 +368,8 @@ class MuJoCoRL:
         obs = self._collect_obs(extra)
         if N == 1:
             rewards = {k: (v[0].item() if torch.is_tensor(v) else v) for k, v in rewards.items()}
+            if not self.environment_dynamics and not self.reward_functions:
+                rewards = {k: 0 for k in rewards}   # the reference's untouched `int 0` (mujoco_rl.py:262)
             terms = {k: bool(v[0].item()) for k, v in terms.items()}
             truncs = {k: bool(v[0].item()) for k, v in truncs.items()}
         return obs, rewards, terms, truncs, infos
