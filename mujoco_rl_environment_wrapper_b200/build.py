@@ -43,7 +43,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("MJB_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:

@@ -12,6 +12,10 @@
 #include "env_kernel.cuh"
 #include "mjb_internal.h"
 
+#ifndef MJB_MAX_THREADS
+#define MJB_MAX_THREADS 512
+#endif
+
 namespace mjb {
 
 // ---- TMA bulk copy of the constant image into shared memory (SASS: UBLKCP + SYNCS) ---------------
@@ -44,7 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // One CTA per SM slot, `warps` environments in flight per CTA; each warp walks the env index space
 // with a grid-wide stride (envs are independent, no inter-warp communication after the staging).
 template <bool PHYS, bool PACKED>
-__global__ void __launch_bounds__(512, PHYS ? 1 : 4) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
+__global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
                       int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env,
                       int lockstep, const int* __restrict__ env_order) {
   extern __shared__ __align__(128) uint32_t smem[];
@@ -229,7 +233,7 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
   size_t sm_smem = prop.sharedMemPerMultiprocessor;
   size_t cta_budget = std::min(max_smem, sm_smem / ctas - 1024);
   int warps = cta_budget > fixed ? (int)((cta_budget - fixed) / per_env) : 0;
-  int cap = mjb::env_int("MJB_WARPS", 16);
+  int cap = std::min(MJB_MAX_THREADS / 32, mjb::env_int("MJB_WARPS", MJB_MAX_THREADS / 32));
   if (warps > cap) warps = cap;
   if (warps < 1) { mjb::set_error("model needs more shared memory per environment than one SM has"); return fail(MJB_ERR_LIMIT); }
   // even out the rounds: the fewest warps per CTA that keeps the same number of passes over the envs
