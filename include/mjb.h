@@ -143,6 +143,8 @@ typedef struct mjb_buffers {
   int32_t* contact_geom; /* [N, maxcon, 2] or NULL */
   float* contact_dist;   /* [N, maxcon] or NULL */
   int32_t* niter;        /* [N] or NULL: Newton iterations of the last forward pass (diagnostic) */
+  int32_t* nreset;       /* [N] or NULL: how often the env was auto-reset because its state became non-finite
+                            (MuJoCo's mj_checkPos / mj_checkVel behaviour: warn and mj_resetData) */
 } mjb_buffers;
 
 /* data_store column ids */

@@ -57,7 +57,7 @@ class Layout(ctypes.Structure):
 class Buffers(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("qpos", "qvel", "ctrl", "warmstart", "sensordata", "probe", "actions", "obs", "reward", "term",
-                 "trunc", "timestep", "store_i", "store_f", "ncon", "contact_geom", "contact_dist", "niter")]
+                 "trunc", "timestep", "store_i", "store_f", "ncon", "contact_geom", "contact_dist", "niter", "nreset")]
 
 
 _LIB = None

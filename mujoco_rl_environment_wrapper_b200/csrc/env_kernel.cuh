@@ -259,6 +259,21 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
   if (PHYS) {
     MJB_NOUNROLL
     for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, &niter);
+    if (integrate) {
+      // MuJoCo's mj_checkPos / mj_checkVel: a non-finite or absurd state resets that env (here: that copy)
+      MJB_NOUNROLL
+      for (int k = 0; k < K; k++) {
+        bool bad = false;
+        for (int j = lane; j < dm.nq1; j += 32) { float x = qpos[k * dm.nq1 + j]; bad |= !(fabsf(x) < 1e10f); }
+        for (int j = lane; j < dm.nv1; j += 32) { float x = qvel[k * dm.nv1 + j]; bad |= !(fabsf(x) < 1e10f); }
+        if (MJB_BALLOT(bad)) {   // warp-uniform
+          for (int j = lane; j < dm.nq1; j += 32) qpos[k * dm.nq1 + j] = CF(qpos0)[k * dm.nq1 + j];
+          for (int j = lane; j < dm.nv1; j += 32) { qvel[k * dm.nv1 + j] = 0.f; qacc[k * dm.nv1 + j] = 0.f; }
+          if (B.nreset && lane == 0 && ((upd >> k) & 1u)) B.nreset[e0 + k] += 1;
+        }
+      }
+      MJB_SYNC();
+    }
   }
   if (ncon >= 0 && (B.ncon || B.contact_geom) && K == 1) {
     const uint32_t* pairs = CU(pair_pack);

@@ -145,3 +145,23 @@ def test_packed_envs_ragged_count_and_masked_reset():
             assert not eb.store_i[e, :, :5].any()
         else:
             assert np.array_equal(eb.qpos[e], q_before[e]) and eb.timestep[e] == 6
+
+
+def test_non_finite_state_resets_only_that_env():
+    """mj_checkPos / mj_checkVel behaviour: an env whose state became NaN / absurd is reset to qpos0 (counted in
+    `nreset`); its warp neighbour in a packed pair is untouched."""
+    model, tables, agents, fj = load_scene("1A")
+    spec, keep = make_spec(model, tables, agents, fj)
+    eb = E.EmuBatch(model.blob, spec, 3, keep)
+    eb.run(E.MODE_RESET)
+    eb.actions[:, :, :8] = 0.3
+    eb.run(E.MODE_PHYSICS, 3)
+    healthy = eb.qpos.copy()
+    eb.qvel[1, 3] = np.nan
+    eb.qpos[2, 0] = 3e12
+    eb.run(E.MODE_PHYSICS, 1)
+    assert list(eb.nreset) == [0, 1, 1]
+    for e in (1, 2):
+        assert np.allclose(eb.qpos[e, :15], model.fields["qpos0"], atol=1e-6) and not eb.qvel[e].any()
+    assert np.isfinite(eb.qpos).all() and np.isfinite(eb.qvel).all()
+    assert not np.array_equal(eb.qpos[0], healthy[0]) and abs(eb.qpos[0, 2] - healthy[0, 2]) < 0.1
