@@ -28,12 +28,21 @@ class Batch:
         A, N, dev = spec.n_agents, self.num_envs, self.device
         f32, i32, u8 = torch.float32, torch.int32, torch.uint8
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        # the step's results (obs, reward, term, trunc) live back to back in ONE allocation so that the host-buffer
+        # entry point can return them with a single device-to-host copy
+        nb = [N * max(1, A) * lay.obs_stride * 4, N * max(1, A) * 4, N * (A + 1), N * (A + 1)]
+        self._out_block = torch.zeros(sum((b + 15) // 16 * 16 for b in nb) , dtype=u8, device=dev)
+        offs, o = [], 0
+        for b in nb:
+            offs.append(o)
+            o += (b + 15) // 16 * 16
+        view = lambda k, dt, shape: self._out_block[offs[k]:offs[k] + nb[k]].view(dt).view(shape)
         self.buf = {
             "qpos": z((N, lay.qpos_stride), f32), "qvel": z((N, lay.qvel_stride), f32),
             "ctrl": z((N, lay.ctrl_stride), f32), "warmstart": z((N, lay.qvel_stride), f32),
             "sensordata": z((N, lay.sensor_stride), f32), "probe": z((N, max(1, lay.probe_count), 4), f32),
-            "actions": z((N, max(1, A), lay.act_stride), f32), "obs": z((N, max(1, A), lay.obs_stride), f32),
-            "reward": z((N, max(1, A)), f32), "term": z((N, A + 1), u8), "trunc": z((N, A + 1), u8),
+            "actions": z((N, max(1, A), lay.act_stride), f32), "obs": view(0, f32, (N, max(1, A), lay.obs_stride)),
+            "reward": view(1, f32, (N, max(1, A))), "term": view(2, u8, (N, A + 1)), "trunc": view(3, u8, (N, A + 1)),
             "timestep": z((N,), i32), "store_i": z((N, max(1, A), lay.store_i32), i32),
             "store_f": z((N, max(1, A), lay.store_f32), f32), "ncon": z((N,), i32),
             "contact_geom": z((N, lay.maxcon, 2), i32), "contact_dist": z((N, lay.maxcon), f32), "niter": z((N,), i32), "nreset": z((N,), i32),
@@ -104,10 +113,19 @@ class Batch:
         """(actions, obs, reward, term, trunc) host arrays for step_host.  Page-locked by default: the library
         then copies straight to / from them; pageable arrays work too (staged through pinned memory)."""
         lay, A, N = self.layout, self.spec.n_agents, self.num_envs
-        shapes = [((N, A, lay.act_stride), torch.float32), ((N, A, lay.obs_stride), torch.float32), ((N, A), torch.float32),
-                  ((N, A + 1), torch.uint8), ((N, A + 1), torch.uint8)]
-        self._host_keep = [torch.zeros(s, dtype=d, pin_memory=pinned) for s, d in shapes]
-        return tuple(t.numpy() for t in self._host_keep)
+        act = torch.zeros((N, A, lay.act_stride), dtype=torch.float32, pin_memory=pinned)
+        # results mirror the device block (same 16-byte aligned offsets): one D2H copy brings all four back
+        nb = [N * A * lay.obs_stride * 4, N * A * 4, N * (A + 1), N * (A + 1)]
+        block = torch.zeros(sum((b + 15) // 16 * 16 for b in nb), dtype=torch.uint8, pin_memory=pinned)
+        offs, o = [], 0
+        for b in nb:
+            offs.append(o)
+            o += (b + 15) // 16 * 16
+        views = [block[offs[0]:offs[0] + nb[0]].view(torch.float32).view(N, A, lay.obs_stride),
+                 block[offs[1]:offs[1] + nb[1]].view(torch.float32).view(N, A),
+                 block[offs[2]:offs[2] + nb[2]].view(N, A + 1), block[offs[3]:offs[3] + nb[3]].view(N, A + 1)]
+        self._host_keep = [act, block] + views
+        return (act.numpy(),) + tuple(v.numpy() for v in views)
 
     @property
     def launch_count(self):

@@ -350,10 +350,21 @@ int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward,
   CUDA_TRY(cudaMemcpyAsync(b->B.actions, direct ? actions : b->h_act, nb_act, cudaMemcpyHostToDevice, b->stream));
   int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr);
   if (rc != MJB_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(direct ? obs : b->h_obs, b->B.obs, nb_obs, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(direct ? reward : b->h_rew, b->B.reward, nb_rew, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(direct ? term : b->h_term, b->B.term, nb_flag, cudaMemcpyDeviceToHost, b->stream));
-  CUDA_TRY(cudaMemcpyAsync(direct ? trunc : b->h_trunc, b->B.trunc, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+  // when the four result arrays sit back to back (16-byte aligned) on both sides, one copy returns them all
+  auto r16 = [](size_t n) { return (n + 15) / 16 * 16; };
+  const char *d0 = (const char*)b->B.obs, *h0 = (const char*)obs;
+  const bool packed_out = direct && (const char*)b->B.reward == d0 + r16(nb_obs) && (const char*)reward == h0 + r16(nb_obs) &&
+                          (const char*)b->B.term == d0 + r16(nb_obs) + r16(nb_rew) && (const char*)term == h0 + r16(nb_obs) + r16(nb_rew) &&
+                          (const char*)b->B.trunc == d0 + r16(nb_obs) + r16(nb_rew) + r16(nb_flag) &&
+                          (const char*)trunc == h0 + r16(nb_obs) + r16(nb_rew) + r16(nb_flag);
+  if (packed_out) {
+    CUDA_TRY(cudaMemcpyAsync(obs, b->B.obs, r16(nb_obs) + r16(nb_rew) + r16(nb_flag) + nb_flag, cudaMemcpyDeviceToHost, b->stream));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(direct ? obs : b->h_obs, b->B.obs, nb_obs, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(direct ? reward : b->h_rew, b->B.reward, nb_rew, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(direct ? term : b->h_term, b->B.term, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(direct ? trunc : b->h_trunc, b->B.trunc, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   if (!direct) {
     memcpy(obs, b->h_obs, nb_obs);
