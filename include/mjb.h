@@ -110,7 +110,11 @@ typedef struct mjb_env_spec {
   uint64_t seed;                      /* counter-based stream replacing random.randint (README.md:154) */
   int32_t solver_iterations;          /* fixed Newton iteration count per substep (0 = library default) */
   int32_t ls_iterations;              /* fixed line-search iterations (0 = default) */
+  int32_t flags;                      /* MJB_SPEC_* bits */
 } mjb_env_spec;
+
+/* mjb_env_spec.flags */
+enum { MJB_SPEC_NO_PACK = 1 /* one env per warp even for small models (needed by mjb_set_env_subset) */ };
 
 /* Caller-owned device buffers (torch CUDA tensors on the Python side).  Row-major, env-major;
  * strides are in elements and come from mjb_batch_layout. Optional pointers may be NULL. */
@@ -181,6 +185,12 @@ int mjb_kernel_time_ms(mjb_batch* b, double* total_ms, int64_t* launches);
  * share an SM round, so ordering envs by their last solver cost (buffers.niter) evens the rounds out.
  * Results do not depend on it (envs are independent). */
 int mjb_set_env_order(mjb_batch* b, const int32_t* order_dev);
+/* Level variants (the reference's `xmlPath` list, mujoco_parent.py:88-91,351-356): several batch handles, one
+ * per level, are created over the SAME caller-owned buffers; each then steps / resets only the envs currently
+ * assigned to its level.  `env_ids_dev` lists `count` distinct env indices in [0, num_envs) (device memory,
+ * must stay valid until replaced); NULL restores "all envs".  Needs a batch created with MJB_SPEC_NO_PACK.
+ * A reset mask stays indexed by env id. */
+int mjb_set_env_subset(mjb_batch* b, const int32_t* env_ids_dev, int32_t count);
 /* launch geometry chosen at creation: CTAs, env-warps per CTA, dynamic shared memory per CTA */
 int mjb_batch_geometry(const mjb_batch* b, int32_t* grid, int32_t* warps_per_cta, int64_t* smem_bytes);
 /* counter-based draw used for target selection: exported so tests can reproduce the stream */

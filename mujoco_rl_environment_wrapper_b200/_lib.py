@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmjb.so")
 
 MAX_AGENTS, MAX_PLUGINS, MAX_TARGETS = 8, 4, 16
+SPEC_NO_PACK = 1   # mjb_env_spec.flags
 OBJ_BODY, OBJ_JOINT, OBJ_GEOM, OBJ_SITE, OBJ_ACTUATOR, OBJ_SENSOR = 1, 3, 5, 6, 19, 20
 DYN_LANGUAGE, DYN_PICKUP = 1, 2
 REW_TAG_DISTANCE, REW_ANT = 1, 2
@@ -44,7 +45,7 @@ class EnvSpec(ctypes.Structure):
         ("n_targets", ctypes.c_int32),
         ("target_objtype", ctypes.c_int32 * MAX_TARGETS), ("target_objid", ctypes.c_int32 * MAX_TARGETS),
         ("seed", ctypes.c_uint64),
-        ("solver_iterations", ctypes.c_int32), ("ls_iterations", ctypes.c_int32),
+        ("solver_iterations", ctypes.c_int32), ("ls_iterations", ctypes.c_int32), ("flags", ctypes.c_int32),
     ]
 
 
@@ -108,6 +109,7 @@ def load(build_if_missing=True):
     lib.mjb_set_timing.argtypes = [vp, i32]
     lib.mjb_kernel_time_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.mjb_set_env_order.argtypes = [vp, vp]
+    lib.mjb_set_env_subset.argtypes = [vp, vp, ctypes.c_int32]
     lib.mjb_batch_geometry.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)]
     lib.mjb_draw_u32.restype = ctypes.c_uint32
     lib.mjb_draw_u32.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]

@@ -14,7 +14,9 @@ from . import _lib as L
 
 
 class Batch:
-    def __init__(self, model: "L.Model", spec: "L.EnvSpec", num_envs: int, device=None, keepalive=()):
+    def __init__(self, model: "L.Model", spec: "L.EnvSpec", num_envs: int, device=None, keepalive=(), share=None):
+        """`share`: another Batch whose tensors this handle steps as well (level variants, see set_subset);
+        the two models must produce the same buffer layout."""
         self._lib = L.load()
         if not torch.cuda.is_available():
             raise RuntimeError("mujoco_rl_environment_wrapper_b200: no CUDA device — the step path is CUDA-only "
@@ -25,19 +27,23 @@ class Batch:
         lay = L.Layout()
         L.check(self._lib.mjb_batch_layout(model._h, ctypes.byref(spec), self.num_envs, ctypes.byref(lay)), "batch layout")
         self.layout = lay
+        if share is not None:
+            same = all(getattr(lay, f) == getattr(share.layout, f) for f, _ in L.Layout._fields_)
+            if not same or share.num_envs != self.num_envs or share.device != self.device:
+                raise Exception("level variants must share one buffer layout (same sizes, sensors, agents and plugins)")
         A, N, dev = spec.n_agents, self.num_envs, self.device
         f32, i32, u8 = torch.float32, torch.int32, torch.uint8
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
         # the step's results (obs, reward, term, trunc) live back to back in ONE allocation so that the host-buffer
         # entry point can return them with a single device-to-host copy
         nb = [N * max(1, A) * lay.obs_stride * 4, N * max(1, A) * 4, N * (A + 1), N * (A + 1)]
-        self._out_block = torch.zeros(sum((b + 15) // 16 * 16 for b in nb) , dtype=u8, device=dev)
+        self._out_block = share._out_block if share is not None else torch.zeros(sum((b + 15) // 16 * 16 for b in nb) , dtype=u8, device=dev)
         offs, o = [], 0
         for b in nb:
             offs.append(o)
             o += (b + 15) // 16 * 16
         view = lambda k, dt, shape: self._out_block[offs[k]:offs[k] + nb[k]].view(dt).view(shape)
-        self.buf = {
+        self.buf = share.buf if share is not None else {
             "qpos": z((N, lay.qpos_stride), f32), "qvel": z((N, lay.qvel_stride), f32),
             "ctrl": z((N, lay.ctrl_stride), f32), "warmstart": z((N, lay.qvel_stride), f32),
             "sensordata": z((N, lay.sensor_stride), f32), "probe": z((N, max(1, lay.probe_count), 4), f32),
@@ -94,6 +100,16 @@ class Batch:
         key = self.buf["niter"] * 64 + self.buf["ncon"]
         self._order = torch.argsort(key).to(torch.int32)
         L.check(self._lib.mjb_set_env_order(self._h, ctypes.c_void_p(self._order.data_ptr())), "env order")
+
+    def set_subset(self, env_ids=None):
+        """Restrict this handle's launches to the listed env indices (int32 CUDA tensor; None = all envs)."""
+        if env_ids is None:
+            self._subset = None
+            L.check(self._lib.mjb_set_env_subset(self._h, None, 0), "env subset")
+            return
+        self._subset = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        L.check(self._lib.mjb_set_env_subset(self._h, ctypes.c_void_p(self._subset.data_ptr()), int(self._subset.numel())),
+                "env subset")
 
     def physics(self, skip_frames=1):
         L.check(self._lib.mjb_physics(self._h, skip_frames), "physics")

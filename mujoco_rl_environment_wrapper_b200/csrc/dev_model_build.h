@@ -496,6 +496,7 @@ inline int choose_pack(const HostModel& host, const mjb_env_spec& spec, int num_
   K = std::min(K, env_int("MJB_PACK", 4));
   K = std::min(K, num_envs);
   if (spec.skip_frames == 0) K = 1;   // no physics in the step: nothing to share
+  if (spec.flags & MJB_SPEC_NO_PACK) K = 1;
   return std::max(1, K);
 }
 

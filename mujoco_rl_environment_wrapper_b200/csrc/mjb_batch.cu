@@ -50,7 +50,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <bool PHYS, bool PACKED>
 __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
                       int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env,
-                      int lockstep, const int* __restrict__ env_order) {
+                      int lockstep_groups, const int* __restrict__ env_order, int active) {
+  const int lockstep = lockstep_groups & 0xff, groups = lockstep_groups >> 8;
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* img = smem + 4;  // 16 B after the barrier
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
   //  * dynamic: each warp pulls its next env from a grid-wide counter (better balance, poor i-cache reuse).
   const int stride = gridDim.x * warps;
   const int pack = PACKED ? dm.pack : 1;
-  const int nvirt = (num_envs + pack - 1) / pack;   // virtual envs: `pack` real envs share a warp
+  const int nvirt = (active + pack - 1) / pack;   // virtual envs: `pack` real envs share a warp (active = envs this launch walks)
   const int rounds = (nvirt - blockIdx.x * warps + stride - 1) / stride;
   int env = blockIdx.x * warps + warp;
   for (int r = 0;; r++) {
@@ -88,9 +89,15 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
       // (a masked reset lets warps skip their env, so intra-step alignment is off for it)
       c.cta_threads = (mask == nullptr ? 32 : 0) * (busy > warps ? warps : (busy < 0 ? 0 : busy));
     }
-    if (env < nvirt) run_env<PHYS, PACKED>(c, B, (lockstep && env_order) ? env_order[env] : env, num_envs, mode, skip_frames, mask);
+    if (env < nvirt) run_env<PHYS, PACKED>(c, B, env_order ? env_order[env] : env, num_envs, mode, skip_frames, mask);
     if (lockstep) {
-      if (lockstep != 3) __syncthreads();   // mode 3 aligns inside the step (before the collision phase) instead
+      if (groups > 1) {
+        // the env-warps re-align in `groups` independent sets: fewer warps wait on the slowest env of a round,
+        // at the price of `groups` instruction streams per SM
+        const int gsz = (warps + groups - 1) / groups, g = warp / gsz;
+        const int cnt = 32 * (g * gsz + gsz <= warps ? gsz : warps - g * gsz);
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "r"(cnt) : "memory");
+      } else if (lockstep != 3) __syncthreads();   // mode 3 aligns inside the step (before the collision phase) instead
       env += stride;
     } else {
       __syncwarp();
@@ -117,8 +124,10 @@ struct mjb_batch {
   uint32_t* d_image = nullptr;
   int* d_next = nullptr;   // ring of work counters, one per in-flight launch
   int next_slot = 0;
-  int lockstep = 0;
-  const int* env_order = nullptr;
+  int lockstep = 0, groups = 1;
+  const int* env_order = nullptr;   // scheduling permutation of all envs ...
+  const int* subset = nullptr;      // ... or the env ids of this handle's level
+  int subset_count = -1;
   int64_t launches = 0;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -140,6 +149,7 @@ namespace {
   } while (0)
 
 int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
+  if (b->subset && b->subset_count == 0) return MJB_OK;   // no env on this level right now
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (b->timing) {
     CUDA_TRY(cudaEventCreate(&e0));
@@ -156,12 +166,14 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
   if (mode == mjb::MODE_STEP && b->has_lite) {
     // no physics in the step: many small envs per SM, rounds aligned the same way
     mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, b->stream>>>(b->lite.dm, b->d_image, b->B, b->num_envs, mode,
-                                                                                      skip_frames, mask, counter, 2, nullptr);
+                                                                                      skip_frames, mask, counter, 2, b->subset,
+                                                                                      b->subset ? b->subset_count : b->num_envs);
   } else {
     auto kern = b->img.dm.pack > 1 ? mjb::k_env<true, true> : mjb::k_env<true, false>;
     kern<<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode, skip_frames, mask,
-                                                                counter, b->lockstep,
-                                                                (b->lockstep && b->img.dm.pack == 1) ? b->env_order : nullptr);
+                                                                counter, b->lockstep | (b->groups << 8),
+                                                                b->subset ? b->subset : ((b->lockstep && b->img.dm.pack == 1) ? b->env_order : nullptr),
+                                                                b->subset ? b->subset_count : b->num_envs);
   }
   CUDA_TRY(cudaGetLastError());
   if (b->timing) {
@@ -279,6 +291,8 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
   }
   b->h_first[0] = b->grid * b->warps;
   b->lockstep = mjb::env_int("MJB_LOCKSTEP", 2);
+  b->groups = mjb::env_int("MJB_GROUPS", 1);
+  if (b->groups < 1 || b->groups > 8 || b->lockstep != 2) b->groups = 1;
   const int A = dm.n_agents;
   if (cudaMallocHost(&b->h_act, sizeof(float) * (size_t)num_envs * A * dm.act_stride + 16) != cudaSuccess ||
       cudaMallocHost(&b->h_obs, sizeof(float) * (size_t)num_envs * A * dm.obs_stride + 16) != cudaSuccess ||
@@ -401,6 +415,18 @@ int mjb_kernel_time_ms(mjb_batch* b, double* total_ms, int64_t* launches) {
 int mjb_set_env_order(mjb_batch* b, const int32_t* order_dev) {
   if (!b) { mjb::set_error("mjb_set_env_order: null batch"); return MJB_ERR_ARG; }
   b->env_order = order_dev;
+  return MJB_OK;
+}
+
+int mjb_set_env_subset(mjb_batch* b, const int32_t* env_ids_dev, int32_t count) {
+  if (!b) { mjb::set_error("mjb_set_env_subset: null batch"); return MJB_ERR_ARG; }
+  if (!env_ids_dev) { b->subset = nullptr; b->subset_count = -1; return MJB_OK; }
+  if (count < 0 || count > b->num_envs) { mjb::set_error("mjb_set_env_subset: count out of range"); return MJB_ERR_ARG; }
+  if (b->img.dm.pack != 1) {
+    mjb::set_error("mjb_set_env_subset: the batch packs several envs per warp; create it with MJB_SPEC_NO_PACK");
+    return MJB_ERR_ARG;
+  }
+  b->subset = env_ids_dev; b->subset_count = count;
   return MJB_OK;
 }
 

@@ -81,13 +81,31 @@ class MuJoCoRL:
 
         self.timestep = 0
         self.action_routing = {"physical": [], "dynamic": {}}
-        # xml (str or list -> random.choice, mujoco_parent.py:88-91)
-        self.xml_path = self.xml_paths if isinstance(self.xml_paths, str) else random.choice(self.xml_paths)
-        with open(self.xml_path, "r") as fh:
-            self._xml_text = fh.read()
-        self.model = L.Model(self._xml_text)
-        self.__instantiate_json()
-        self._tables = Tables(self._xml_text, self.model, self.agents, self.free_joint)
+        # xml: str, or list = level variants re-drawn at every reset (mujoco_parent.py:88-91, 351-356).  Every level
+        # is compiled once; with num_envs > 1 each env carries its own level id.
+        self._level_paths = [self.xml_paths] if isinstance(self.xml_paths, str) else list(self.xml_paths)
+        if isinstance(self.info_jsons, list) and len(self.info_jsons) != len(self._level_paths):
+            raise Exception("Length mismatch between info_json list and xml_paths list")
+        self._level_rng = np.random.default_rng(self.seed)
+        self._levels = []
+        for path in self._level_paths:
+            with open(path, "r") as fh:
+                text = fh.read()
+            model = L.Model(text)
+            tables = Tables(text, model, self.agents, self.free_joint)
+            info_json, names = self.__load_json(path)
+            self._levels.append({"xml_path": path, "xml_text": text, "model": model, "tables": tables,
+                                 "info_json": info_json, "info_name_list": names})
+        first = self._levels[0]["tables"]
+        for lv in self._levels[1:]:
+            t, m, m0 = lv["tables"], lv["model"], self._levels[0]["model"]
+            if (t.agents_action_index != first.agents_action_index or t.agents_observation_index != first.agents_observation_index
+                    or t.obs_space != first.obs_space or t.act_space != first.act_space
+                    or (m.nq, m.nv, m.nu, m.nsensordata) != (m0.nq, m0.nv, m0.nu, m0.nsensordata)):
+                raise Exception(f"level '{lv['xml_path']}' is not structurally identical to '{self._levels[0]['xml_path']}' "
+                                f"(the reference builds its index tables once and reuses them for every level)")
+        self._first_level = self._level_paths.index(random.choice(self._level_paths)) if self.num_envs == 1 else 0
+        self._use_level(self._first_level)
         self.agents_action_index = self._tables.agents_action_index
         self.agents_observation_index = self._tables.agents_observation_index
 
@@ -101,27 +119,28 @@ class MuJoCoRL:
         self._wipe_store()
 
     # ------------------------------------------------------------------------------------------
-    def __instantiate_json(self):
-        """mujoco_rl.py:93-112"""
-        if isinstance(self.info_jsons, list):
-            if len(self.info_jsons) != len(self.xml_paths):
-                raise Exception("Length mismatch between info_json list and xml_paths list")
-            tail = os.path.split(self.xml_path)[1]
-            json_file = tail.split(".")[0] + ".json"
-            json_file = [cur for cur in self.info_jsons if json_file in cur][0]
-            with open(json_file) as fh:
-                self.info_json = json.load(fh)
-            self.info_name_list = list(self.info_json["environment"]["objects"].keys())
-        elif isinstance(self.info_jsons, str):
-            with open(self.info_jsons) as fh:
-                self.info_json = json.load(fh)
-            self.info_name_list = list(self.info_json["environment"]["objects"].keys())
-        elif isinstance(self.info_jsons, dict):  # convenience: already-parsed json
-            self.info_json = self.info_jsons
-            self.info_name_list = list(self.info_json["environment"]["objects"].keys())
+    def __load_json(self, xml_path):
+        """mujoco_rl.py:93-112: the info JSON that belongs to `xml_path` (list entries are matched by file stem)"""
+        src = self.info_jsons
+        if isinstance(src, list):
+            stem = os.path.split(xml_path)[1].split(".")[0] + ".json"
+            src = [cur for cur in src if stem in cur][0]
+        if isinstance(src, str):
+            with open(src) as fh:
+                info = json.load(fh)
+        elif isinstance(src, dict):  # convenience: already-parsed json
+            info = src
         else:
-            self.info_json = None
-            self.info_name_list = []
+            return None, []
+        return info, list(info["environment"]["objects"].keys())
+
+    def _use_level(self, lid):
+        """the attributes the reference re-binds when it (re)loads a level (mujoco_parent.py:351-356, mujoco_rl.py:304-310)"""
+        lv = self._levels[lid]
+        self.xml_path, self._xml_text, self.model, self._tables = lv["xml_path"], lv["xml_text"], lv["model"], lv["tables"]
+        self.info_json, self.info_name_list = lv["info_json"], lv["info_name_list"]
+        if "probe_names" in lv:
+            self._target_names, self._probe_names = lv["target_names"], lv["probe_names"]
 
     def __build_spaces(self):
         """mujoco_rl.py:171-213"""
@@ -178,6 +197,47 @@ class MuJoCoRL:
         raise KeyError(f"Invalid name '{name}': neither a body nor a geom")
 
     def __build_batch(self):
+        """one spec + batch handle per level over ONE set of tensors; single-level envs keep env packing"""
+        multi = len(self._levels) > 1
+        for lid, lv in enumerate(self._levels):
+            self._use_level(lid)
+            spec, keep = self.__build_spec()
+            if multi:
+                spec.flags |= L.SPEC_NO_PACK
+            lv["spec"], lv["target_names"], lv["probe_names"] = spec, self._target_names, self._probe_names
+            with torch.cuda.device(self.device):
+                lv["batch"] = Batch(self.model, spec, self.num_envs, device=self.device, keepalive=keep,
+                                    share=self._levels[0]["batch"] if lid else None)
+        self._use_level(0)
+        self._spec, self._batch = self._levels[0]["spec"], self._levels[0]["batch"]
+        self.level_id = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._level_host = np.zeros(self.num_envs, dtype=np.int64)
+        if multi:
+            self._draw_levels(None, first=True)
+        self._sample_gen = torch.Generator(device=self.device)
+        self._sample_gen.manual_seed(self.seed)
+        self._act_low = torch.tensor(np.asarray(self._action_space[self.agents[0]].low), device=self.device)
+        self._act_high = torch.tensor(np.asarray(self._action_space[self.agents[0]].high), device=self.device)
+
+    def _draw_levels(self, mask, first=False):
+        """a fresh level for every env being reset (the reference's random.choice at reset, mujoco_parent.py:351-352),
+        then each level's handle is pointed at the envs it owns.  Host-side: resets are rare next to steps."""
+        n_lv = len(self._levels)
+        if self.num_envs == 1:   # one env: the reference's own draw (global `random`), already made once by __init__
+            draw = np.array([self._first_level if first else self._level_paths.index(random.choice(self._level_paths))])
+        else:
+            draw = self._level_rng.integers(0, n_lv, size=self.num_envs)
+        if mask is None:
+            self._level_host = draw
+        else:
+            m = mask.detach().to("cpu").numpy().astype(bool).reshape(-1)
+            self._level_host = np.where(m, draw, self._level_host)
+        self.level_id.copy_(torch.from_numpy(self._level_host.astype(np.int32)))
+        for lid, lv in enumerate(self._levels):
+            lv["batch"].set_subset(torch.from_numpy(np.nonzero(self._level_host == lid)[0].astype(np.int32)))
+        self._use_level(int(self._level_host[0]))
+
+    def __build_spec(self):
         A = len(self.agents)
         spec = L.EnvSpec()
         spec.n_agents, spec.free_joint = A, int(bool(self.free_joint))
@@ -250,13 +310,7 @@ class MuJoCoRL:
         self._oi = (ctypes.c_int32 * max(1, len(obs_index)))(*obs_index)
         spec.act_index = ctypes.cast(self._ai, ctypes.POINTER(ctypes.c_int32))
         spec.obs_index = ctypes.cast(self._oi, ctypes.POINTER(ctypes.c_int32))
-        self._spec = spec
-        with torch.cuda.device(self.device):
-            self._batch = Batch(self.model, spec, self.num_envs, device=self.device, keepalive=(self._ai, self._oi))
-        self._sample_gen = torch.Generator(device=self.device)
-        self._sample_gen.manual_seed(self.seed)
-        self._act_low = torch.tensor(np.asarray(self._action_space[self.agents[0]].low), device=self.device)
-        self._act_high = torch.tensor(np.asarray(self._action_space[self.agents[0]].high), device=self.device)
+        return spec, (self._ai, self._oi)
 
     # ---- validators (mujoco_rl.py:114-169): run each plugin once for agents[0]
     def __check_dynamics(self, dynamics):
@@ -340,7 +394,8 @@ class MuJoCoRL:
         """mujoco_rl.py:243-289 for all envs at once (one fused kernel launch)."""
         b = self._batch
         self._load_actions(action)
-        b.step()
+        for lv in self._levels:
+            lv["batch"].step()
         N = self.num_envs
         rewards = {agent: b.reward[:, a] for a, agent in enumerate(self.agents)}
         terms = {agent: b.term[:, a].bool() for a, agent in enumerate(self.agents)}
@@ -378,7 +433,10 @@ class MuJoCoRL:
         """mujoco_rl.py:291-331.  `mask` (bool[N]) resets a subset of envs (new; the reference has one env)."""
         b = self._batch
         b.actions[:, :, :self._act_dim] = self.sample_actions()  # the reference applies dynamics once with a sampled action
-        b.reset(mask)
+        if len(self._levels) > 1:
+            self._draw_levels(mask)
+        for lv in self._levels:
+            lv["batch"].reset(mask)
         for st in self.data_store.values():
             st.clear()
         infos = {agent: {dyn.__class__.__name__: {} for dyn in self._fused_dyn} for agent in self.agents}

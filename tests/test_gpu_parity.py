@@ -465,3 +465,108 @@ def test_inter_ant_contacts_couple_the_trees():
         assert rel_err(q[e, :30], post["qpos"]) < RTOL, e
         assert rel_err(v[e, :28], post["qvel"]) < RTOL, e
         assert sorted((int(a), int(c_)) for a, c_ in cg[e, :ncon[e]]) == post["pairs"], e
+
+
+# ---- level variants (`xmlPath` list re-drawn at reset, mujoco_parent.py:88-91,351-356)
+def _level_variants(tmp_path):
+    """two structurally identical levels: B moves / shrinks the target boxes and names other targets"""
+    import json
+    import os
+    lv = os.path.join(os.path.dirname(__file__), "levels")
+    a = open(os.path.join(lv, "two_ants.xml")).read()
+    b = a.replace('pos="7.02852 -2.071592 0.4710507"', 'pos="3.5 1.25 0.4710507"').replace(
+        'size="1 1 0.5" rgba="255 0 0 1"', 'size="0.6 0.8 0.5" rgba="0 255 0 1"')
+    assert a != b
+    ja = json.load(open(os.path.join(lv, "info_2A.json")))
+    jb = {"environment": {"objects": {"choice_1": {"tags": ["target"]}, "choice_2": {"tags": []},
+                                      "reference": {"tags": ["target"]}}}, "areas": {}}
+    paths = []
+    for name, xml, js in (("LevelA", a, ja), ("LevelB", b, jb)):
+        open(tmp_path / f"{name}.xml", "w").write(xml)
+        json.dump(js, open(tmp_path / f"{name}.json", "w"))
+        paths.append((str(tmp_path / f"{name}.xml"), str(tmp_path / f"{name}.json")))
+    return paths
+
+
+@pytest.mark.gpu
+def test_level_variants_match_single_level_envs(tmp_path):
+    from mujoco_rl_environment_wrapper_b200 import plugins as P
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    (xa, ja), (xb, jb) = _level_variants(tmp_path)
+    N = 96
+    common = dict(agents=["sender", "receiver"], environmentDynamics=[P.Language], rewardFunctions=[P.tag_distance_reward],
+                  doneFunctions=[P.distance_done], num_envs=N, seed=7)
+    multi = MuJoCoRL(dict(common, xmlPath=[xa, xb], infoJson=[ja, jb]))
+    singles = [MuJoCoRL(dict(common, xmlPath=xa, infoJson=ja)), MuJoCoRL(dict(common, xmlPath=xb, infoJson=jb))]
+    envs = [multi] + singles
+    for e in envs:
+        e.reset()
+    lid = multi.level_id.cpu().numpy()
+    assert set(lid.tolist()) == {0, 1}, "the draw must use both levels"
+
+    def check(tag):
+        for name in ("qpos", "qvel", "obs", "reward", "term", "trunc", "store_i", "store_f", "timestep"):
+            got = getattr(multi.batch, name).cpu().numpy()
+            want = np.where(lid.reshape((-1,) + (1,) * (got.ndim - 1)) == 0, getattr(singles[0].batch, name).cpu().numpy(),
+                            getattr(singles[1].batch, name).cpu().numpy())
+            assert np.array_equal(got, want), f"{tag}: {name} differs from the single-level env of the same level"
+
+    check("reset")
+    for t in range(40):
+        acts = [e.sample_actions() for e in envs]
+        assert torch.equal(acts[0], acts[1]) and torch.equal(acts[0], acts[2])
+        for e, a in zip(envs, acts):
+            e.step(a)
+        check(f"step {t}")
+    # the two levels really differ (the moved box is where ants of level B collide / measure distances)
+    assert not np.array_equal(singles[0].batch.store_f.cpu().numpy(), singles[1].batch.store_f.cpu().numpy())
+
+    # masked reset: only the masked envs get a new level and a fresh state
+    before = {k: getattr(multi.batch, k).clone() for k in ("qpos", "qvel", "timestep")}
+    mask = torch.zeros(N, dtype=torch.bool)
+    mask[::3] = True
+    multi.reset(mask=mask)
+    lid2 = multi.level_id.cpu().numpy()
+    m = mask.numpy()
+    assert np.array_equal(lid2[~m], lid[~m])
+    assert (lid2[m] != lid[m]).any(), "some masked env should have moved to the other level"
+    for k, v in before.items():
+        assert torch.equal(getattr(multi.batch, k)[~mask], v[~mask]), f"{k} of unmasked envs must not change"
+    assert int(multi.batch.timestep[mask].abs().sum()) == 0
+    singles[0].reset()   # qpos0 is the same in both levels (only static boxes moved)
+    assert torch.equal(multi.batch.qpos[mask], singles[0].batch.qpos[mask])
+    for t in range(5):  # and the mixed batch keeps stepping
+        multi.step(multi.sample_actions())
+    assert torch.isfinite(multi.batch.qpos).all()
+
+
+@pytest.mark.gpu
+def test_level_variants_single_env_follows_reference_draw(tmp_path):
+    """num_envs = 1: the level is random.choice(xmlPath) at construction and again at every reset, and the env's
+    `xml_path`, `info_json`, `info_name_list` follow it (mujoco_parent.py:88-91,351-352; mujoco_rl.py:304-310)"""
+    import random
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    (xa, ja), (xb, jb) = _level_variants(tmp_path)
+    random.seed(3)
+    expect = [random.choice([xa, xb]) for _ in range(7)]
+    random.seed(3)
+    env = MuJoCoRL({"xmlPath": [xa, xb], "infoJson": [ja, jb], "agents": ["sender", "receiver"]})
+    seen = [env.xml_path]
+    for _ in range(6):
+        env.reset()
+        seen.append(env.xml_path)
+        want_tags = ["target"] if env.xml_path == xa else []
+        assert env.info_json["environment"]["objects"]["choice_2"]["tags"] == want_tags
+        obs, *_ = env.step({a: env.action_space(a).sample() for a in env.agents})
+        assert obs["sender"].shape == (59,)
+    assert seen == expect and len(set(seen)) == 2
+
+
+@pytest.mark.gpu
+def test_level_variants_reject_structural_mismatch(tmp_path):
+    import os
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    lv = os.path.join(os.path.dirname(__file__), "levels")
+    with pytest.raises(Exception, match="structurally identical"):
+        MuJoCoRL({"xmlPath": [os.path.join(lv, "two_ants.xml"), os.path.join(lv, "two_ants_touch.xml")],
+                  "agents": ["sender", "receiver"], "num_envs": 4})
