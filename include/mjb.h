@@ -47,7 +47,7 @@ typedef struct mjb_batch mjb_batch;
 typedef struct mjb_dims {
   int32_t nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair;
   int32_t integrator;     /* MJB_INT_EULER / MJB_INT_RK4 */
-  int32_t reserved;
+  int32_t ncam;           /* <camera> elements (agent cameras, mujoco_parent.py:505-516) */
   double timestep;
 } mjb_dims;
 
@@ -191,6 +191,12 @@ int mjb_set_env_order(mjb_batch* b, const int32_t* order_dev);
  * must stay valid until replaced); NULL restores "all envs".  Needs a batch created with MJB_SPEC_NO_PACK.
  * A reset mask stays indexed by env id. */
 int mjb_set_env_subset(mjb_batch* b, const int32_t* env_ids_dev, int32_t count);
+/* Agent cameras (`get_camera_data`, mujoco_parent.py:518-556): renders `ncams` fixed cameras (model camera ids,
+ * host array; mjb_name2id with MJB_OBJ_CAMERA) of every env from its current qpos into
+ * rgb_dev = u8 [num_envs, ncams, height, width, 3] (device), rows bottom-up as glReadPixels returns them.
+ * Image formation: first geom hit per pixel, two-sided head-light shading of the geom's rgba (render_kernel.cuh);
+ * the OpenGL pipeline's lights / materials / shadows are not modelled. */
+int mjb_render(mjb_batch* b, const int32_t* cam_ids, int32_t ncams, int32_t width, int32_t height, uint8_t* rgb_dev);
 /* launch geometry chosen at creation: CTAs, env-warps per CTA, dynamic shared memory per CTA */
 int mjb_batch_geometry(const mjb_batch* b, int32_t* grid, int32_t* warps_per_cta, int64_t* smem_bytes);
 /* counter-based draw used for target selection: exported so tests can reproduce the stream */

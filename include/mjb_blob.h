@@ -43,7 +43,7 @@ enum { MJB_GEOM_PLANE = 0, MJB_GEOM_SPHERE = 2, MJB_GEOM_CAPSULE = 3, MJB_GEOM_B
 enum { MJB_JNT_FREE = 0, MJB_JNT_SLIDE = 2, MJB_JNT_HINGE = 3 };
 enum { MJB_SENS_TOUCH = 0, MJB_SENS_ACCELEROMETER = 1, MJB_SENS_RANGEFINDER = 7,
        MJB_SENS_FRAMEXAXIS = 28, MJB_SENS_FRAMEYAXIS = 29, MJB_SENS_FRAMEZAXIS = 30 };
-enum { MJB_OBJ_BODY = 1, MJB_OBJ_JOINT = 3, MJB_OBJ_GEOM = 5, MJB_OBJ_SITE = 6,
+enum { MJB_OBJ_BODY = 1, MJB_OBJ_JOINT = 3, MJB_OBJ_GEOM = 5, MJB_OBJ_SITE = 6, MJB_OBJ_CAMERA = 7,
        MJB_OBJ_ACTUATOR = 19, MJB_OBJ_SENSOR = 20 };
 enum { MJB_INT_EULER = 0, MJB_INT_RK4 = 1 };
 

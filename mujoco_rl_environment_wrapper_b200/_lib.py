@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libmjb.so")
 
 MAX_AGENTS, MAX_PLUGINS, MAX_TARGETS = 8, 4, 16
 SPEC_NO_PACK = 1   # mjb_env_spec.flags
-OBJ_BODY, OBJ_JOINT, OBJ_GEOM, OBJ_SITE, OBJ_ACTUATOR, OBJ_SENSOR = 1, 3, 5, 6, 19, 20
+OBJ_BODY, OBJ_JOINT, OBJ_GEOM, OBJ_SITE, OBJ_CAMERA, OBJ_ACTUATOR, OBJ_SENSOR = 1, 3, 5, 6, 7, 19, 20
 DYN_LANGUAGE, DYN_PICKUP = 1, 2
 REW_TAG_DISTANCE, REW_ANT = 1, 2
 DONE_DISTANCE_LE = 1
@@ -25,7 +25,7 @@ JNT_FREE, JNT_SLIDE, JNT_HINGE = 0, 2, 3
 class Dims(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "npair",
-                 "integrator", "reserved")] + [("timestep", ctypes.c_double)]
+                 "integrator", "ncam")] + [("timestep", ctypes.c_double)]
 
 
 class Plugin(ctypes.Structure):
@@ -110,6 +110,7 @@ def load(build_if_missing=True):
     lib.mjb_kernel_time_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.mjb_set_env_order.argtypes = [vp, vp]
     lib.mjb_set_env_subset.argtypes = [vp, vp, ctypes.c_int32]
+    lib.mjb_render.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp]
     lib.mjb_batch_geometry.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)]
     lib.mjb_draw_u32.restype = ctypes.c_uint32
     lib.mjb_draw_u32.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
@@ -151,7 +152,7 @@ class Model:
         p = self._lib.mjb_model_blob(h, ctypes.byref(n))
         self.blob = bytes((ctypes.c_char * n.value).from_address(p))
         self.fields = parse_blob(self.blob)
-        for k in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "npair"):
+        for k in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "npair", "ncam"):
             setattr(self, k, getattr(d, k))
         self.timestep = d.timestep
 

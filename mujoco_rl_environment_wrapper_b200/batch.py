@@ -111,6 +111,16 @@ class Batch:
         L.check(self._lib.mjb_set_env_subset(self._h, ctypes.c_void_p(self._subset.data_ptr()), int(self._subset.numel())),
                 "env subset")
 
+    def render(self, cam_ids, width=64, height=64, out=None):
+        """u8 [num_envs, len(cam_ids), height, width, 3] images of the listed fixed cameras at the current qpos
+        (rows bottom-up, like the reference's glReadPixels buffer).  Asynchronous on self.stream."""
+        n = len(cam_ids)
+        if out is None:
+            out = torch.empty((self.num_envs, n, height, width, 3), dtype=torch.uint8, device=self.device)
+        ids = (ctypes.c_int32 * n)(*cam_ids)
+        L.check(self._lib.mjb_render(self._h, ids, n, int(width), int(height), ctypes.c_void_p(out.data_ptr())), "render")
+        return out
+
     def physics(self, skip_frames=1):
         L.check(self._lib.mjb_physics(self._h, skip_frames), "physics")
 

@@ -149,6 +149,18 @@ struct DevModel {
   int qpos_stride, qvel_stride, ctrl_stride, sensor_stride, act_stride, obs_stride, store_i32, store_f32;
 };
 
+// ---- camera rendering (render_kernel.cuh): a second, small constant table next to the image -------------
+// cam record: kernel body (-1 = static: pose already in the world frame), mode (0 fixed), pos[3], quat[4],
+// tan(fovy / 2), 2 pad words; then one clamped RGBA (4 floats) per geom
+enum { CAM_MB = 0, CAM_MODE = 1, CAM_POS = 2, CAM_QUAT = 5, CAM_TANHALF = 9, CAM_STRIDE = 12 };
+struct RenderHdr {
+  int ncam, ngeom;
+  int off_cam, off_rgba;   // word offsets into the table
+  int words;               // multiple of 4
+};
+// per-env geom record the rays walk (built in shared memory after the kinematics pass)
+enum { GL_POS = 0, GL_MAT = 3, GL_SIZE = 12, GL_TYPE = 15, GL_RBOUND = 16, GL_RGB = 17, GL_STRIDE = 20 };
+
 // contact record layout inside SF_con (16 words per contact)
 // (CON_DOFS: the dofs of the contact's mask as up to 16 packed bytes, ascending)
 enum { CON_DIST = 0, CON_POS = 1, CON_FRAME = 4, CON_PAIR = 13, CON_MU = 14, CON_MASK = 15, CON_DOFS = 16, CON_STRIDE = 20 };

@@ -20,6 +20,8 @@ namespace mjb {
 struct DevImage {
   DevModel dm;
   std::vector<uint32_t> words;
+  RenderHdr rhdr{};                // camera table (pack == 1 images of models with cameras)
+  std::vector<uint32_t> render;
 };
 
 namespace detail {
@@ -269,6 +271,30 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
     w.begin(IF_pclass);
     for (auto& c : class_list) for (float v : c) w.f(v);
     if (class_list.empty()) for (int i = 0; i < PC_STRIDE; i++) w.f(0);
+  }
+
+  // ---- camera table (not part of the step image: only the render kernel stages it)
+  out.render.clear();
+  out.rhdr = RenderHdr{};
+  if (m.ncam > 0 && pack == 1) {
+    std::vector<uint32_t>& T = out.render;
+    out.rhdr.ncam = m.ncam; out.rhdr.ngeom = m.ngeom; out.rhdr.off_cam = 0;
+    for (int k = 0; k < m.ncam; k++) {
+      int b = m.cam_bodyid[k];
+      V3 lp(m.cam_pos[3 * k], m.cam_pos[3 * k + 1], m.cam_pos[3 * k + 2]);
+      Quat q{m.cam_quat[4 * k], m.cam_quat[4 * k + 1], m.cam_quat[4 * k + 2], m.cam_quat[4 * k + 3]};
+      if (!moving[b]) { lp = kin.xpos[b] + mulv(kin.xmat[b], lp); q = qnormalized(qmul(kin.xquat[b], q)); }
+      T.push_back((uint32_t)b2k[b]); T.push_back((uint32_t)m.cam_mode[k]);
+      for (int i = 0; i < 3; i++) T.push_back(detail::f2w(lp[i]));
+      T.push_back(detail::f2w(q.w)); T.push_back(detail::f2w(q.x)); T.push_back(detail::f2w(q.y)); T.push_back(detail::f2w(q.z));
+      T.push_back(detail::f2w(std::tan(0.5 * m.cam_fovy[k] * 3.14159265358979323846 / 180.0)));
+      T.push_back(0); T.push_back(0);
+    }
+    out.rhdr.off_rgba = (int)T.size();
+    for (int g = 0; g < m.ngeom; g++)
+      for (int i = 0; i < 4; i++) T.push_back(detail::f2w(std::min(1.0, std::max(0.0, m.geom_rgba[4 * g + i]))));
+    while (T.size() % 4) T.push_back(0);
+    out.rhdr.words = (int)T.size();
   }
 
   // ---- sites / sensors / actuators

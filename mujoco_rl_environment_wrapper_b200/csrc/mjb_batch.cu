@@ -10,6 +10,7 @@
 #include "../../include/mjb.h"
 #include "dev_model_build.h"
 #include "env_kernel.cuh"
+#include "render_kernel.cuh"
 #include "mjb_internal.h"
 
 #ifndef MJB_MAX_THREADS
@@ -125,6 +126,8 @@ struct mjb_batch {
   int* d_next = nullptr;   // ring of work counters, one per in-flight launch
   int next_slot = 0;
   int lockstep = 0, groups = 1;
+  mjb::DevImage rimg;     // camera rendering: one-env-per-CTA image + camera table (models with cameras only)
+  uint32_t *d_rimage = nullptr, *d_rtab = nullptr;
   const int* env_order = nullptr;   // scheduling permutation of all envs ...
   const int* subset = nullptr;      // ... or the env ids of this handle's level
   int subset_count = -1;
@@ -220,6 +223,8 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     mjb::make_packed(m->host, *spec, K, b->packed);
     mjb::ModelView mv(K > 1 ? b->packed.rep.blob.data() : m->host.blob.data());
     mjb::build_dev_model(mv, b->packed.vspec, b->img, false, K);
+    mjb::ModelView mv1(m->host.blob.data());
+    if (mv1.ncam > 0) mjb::build_dev_model(mv1, *spec, b->rimg, false, 1);
   } catch (const std::exception& e) {
     mjb::set_error(e.what());
     delete b;
@@ -310,6 +315,8 @@ void mjb_batch_destroy(mjb_batch* b) {
   if (!b) return;
   for (auto& ev : b->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (b->d_image) cudaFree(b->d_image);
+  if (b->d_rimage) cudaFree(b->d_rimage);
+  if (b->d_rtab) cudaFree(b->d_rtab);
   if (b->d_next) cudaFree(b->d_next);
   if (b->h_first) cudaFreeHost(b->h_first);
   if (b->h_act) cudaFreeHost(b->h_act);
@@ -415,6 +422,44 @@ int mjb_kernel_time_ms(mjb_batch* b, double* total_ms, int64_t* launches) {
 int mjb_set_env_order(mjb_batch* b, const int32_t* order_dev) {
   if (!b) { mjb::set_error("mjb_set_env_order: null batch"); return MJB_ERR_ARG; }
   b->env_order = order_dev;
+  return MJB_OK;
+}
+
+int mjb_render(mjb_batch* b, const int32_t* cam_ids, int32_t ncams, int32_t width, int32_t height, uint8_t* rgb_dev) {
+  if (!b || !cam_ids || !rgb_dev) { mjb::set_error("mjb_render: null argument"); return MJB_ERR_ARG; }
+  const mjb::RenderHdr& rh = b->rimg.rhdr;
+  if (rh.ncam == 0) { mjb::set_error("mjb_render: the model has no <camera>"); return MJB_ERR_ARG; }
+  if (ncams < 1 || ncams > RENDER_MAX_CAMS || width < 1 || height < 1 || width > 4096 || height > 4096) {
+    mjb::set_error("mjb_render: 1.." + std::to_string(RENDER_MAX_CAMS) + " cameras, 1..4096 pixels per side");
+    return MJB_ERR_ARG;
+  }
+  mjb::RenderCams cams{};
+  cams.n = ncams;
+  for (int k = 0; k < ncams; k++) {
+    if (cam_ids[k] < 0 || cam_ids[k] >= rh.ncam) { mjb::set_error("mjb_render: camera id out of range"); return MJB_ERR_ARG; }
+    if (b->rimg.render[rh.off_cam + cam_ids[k] * mjb::CAM_STRIDE + mjb::CAM_MODE] != 0) {
+      mjb::set_error("mjb_render: only mode=\"fixed\" cameras can be rendered");
+      return MJB_ERR_ARG;
+    }
+    cams.id[k] = cam_ids[k];
+  }
+  CUDA_TRY(cudaSetDevice(b->device));
+  const mjb::DevModel& dm = b->rimg.dm;
+  const size_t smem = ((size_t)dm.image_words + dm.env_words + rh.words + (size_t)dm.ngeom * mjb::GL_STRIDE + 12 * RENDER_MAX_CAMS) * 4;
+  if (!b->d_rimage) {
+    CUDA_TRY(cudaMalloc(&b->d_rimage, b->rimg.words.size() * 4));
+    CUDA_TRY(cudaMalloc(&b->d_rtab, b->rimg.render.size() * 4));
+    CUDA_TRY(cudaMemcpy(b->d_rimage, b->rimg.words.data(), b->rimg.words.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b->d_rtab, b->rimg.render.data(), b->rimg.render.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaFuncSetAttribute(mjb::k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
+  const int grid = std::min(b->num_envs, sms * per_sm);
+  mjb::k_render<<<grid, 256, smem, b->stream>>>(dm, b->d_rimage, rh, b->d_rtab, b->B.qpos, b->num_envs, cams, width, height, rgb_dev);
+  CUDA_TRY(cudaGetLastError());
+  b->launches++;
   return MJB_OK;
 }
 

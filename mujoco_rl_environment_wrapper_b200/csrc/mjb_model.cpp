@@ -47,7 +47,7 @@ int mjb_model_dims(const mjb_model* m, mjb_dims* out) {
     out->nbody = h.get_int("nbody"); out->njnt = h.get_int("njnt"); out->ngeom = h.get_int("ngeom");
     out->nsite = h.get_int("nsite"); out->nsensor = h.get_int("nsensor");
     out->nsensordata = h.get_int("nsensordata"); out->npair = h.get_int("npair");
-    out->integrator = h.get_int("opt_integrator");
+    out->integrator = h.get_int("opt_integrator"); out->ncam = h.get_int("ncam");
     out->timestep = h.Fv("opt_timestep")[0];
     return MJB_OK;
   } catch (const std::exception& e) {

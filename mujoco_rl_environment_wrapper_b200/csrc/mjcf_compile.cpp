@@ -124,6 +124,16 @@ Quat read_orientation(const Attrs& a, const CompilerOpts& co) {
     double ang = co.degree ? v[3] * kPi / 180.0 : v[3];
     return qnormalized(qaxisangle(normalized(V3(v[0], v[1], v[2])), ang));
   }
+  if (a.el && a.el->attr("xyaxes")) {
+    auto v = parse_nums(*a.el->attr("xyaxes"));
+    if (v.size() != 6) throw std::runtime_error("MJCF: xyaxes needs 6 numbers");
+    V3 x = normalized(V3(v[0], v[1], v[2])), y(v[3], v[4], v[5]);
+    y = normalized(y - x * dot(x, y));
+    V3 z = cross(x, y);
+    M3 R;
+    for (int r = 0; r < 3; r++) { R(r, 0) = x[r]; R(r, 1) = y[r]; R(r, 2) = z[r]; }
+    return qnormalized(m2q(R));
+  }
   if (a.el && a.el->attr("zaxis")) {
     auto v = parse_nums(*a.el->attr("zaxis"));
     if (v.size() != 3) throw std::runtime_error("MJCF: zaxis needs 3 numbers");
@@ -160,6 +170,9 @@ struct Builder {
       geom_solimp, geom_rgba, geom_density, geom_massattr;
   std::vector<int32_t> site_bodyid, site_type;
   std::vector<double> site_pos, site_quat, site_size;
+  std::vector<int32_t> cam_bodyid, cam_mode;
+  std::vector<double> cam_pos, cam_quat, cam_fovy;
+  std::vector<std::string> cam_name;
 
   explicit Builder(HostModel& m) : M(m) {}
 
@@ -276,6 +289,21 @@ struct Builder {
     site_name.push_back(s->attr("name") ? *s->attr("name") : "");
   }
 
+  // <camera>: body-fixed frame looking along its -z with +y up (MuJoCo's convention); other modes keep their
+  // mode id so that a render request for them can be refused
+  void add_camera(const XmlNode* s, int body) {
+    Attrs a{s, nullptr};
+    std::string mode = a.str("mode", "fixed");
+    cam_mode.push_back(mode == "fixed" ? 0 : 1);
+    cam_bodyid.push_back(body);
+    auto p = a.vec("pos", 3, {0, 0, 0});
+    cam_pos.insert(cam_pos.end(), p.begin(), p.end());
+    Quat q = read_orientation(a, co);
+    cam_quat.insert(cam_quat.end(), {q.w, q.x, q.y, q.z});
+    cam_fovy.push_back(a.num("fovy", 45.0));
+    cam_name.push_back(s->attr("name") ? *s->attr("name") : "");
+  }
+
   // depth-first, pre-order: a body gets its id before its children (MuJoCo's numbering)
   void add_body(const XmlNode* b, int parent) {
     int id = (int)body_parentid.size();
@@ -298,6 +326,7 @@ struct Builder {
       }
       else if (c->tag == "geom") { add_geom(c.get(), id); ng++; }
       else if (c->tag == "site") add_site(c.get(), id);
+      else if (c->tag == "camera") add_camera(c.get(), id);
     }
     body_jntnum.push_back(nj);
     body_geomnum.push_back(ng);
@@ -402,6 +431,7 @@ void compile_mjcf(const std::string& xml_text, HostModel& M) {
   for (auto& c : wb->children) {
     if (c->tag == "geom") { B.add_geom(c.get(), 0); ng0++; }
     else if (c->tag == "site") B.add_site(c.get(), 0);
+    else if (c->tag == "camera") B.add_camera(c.get(), 0);
     else if (c->tag == "joint" || c->tag == "freejoint") throw std::runtime_error("MJCF: joints are not allowed in the world body");
   }
   B.body_geomnum.push_back(ng0);
@@ -687,6 +717,10 @@ void compile_mjcf(const std::string& xml_text, HostModel& M) {
   M.F("pair_margin") = pair_margin; M.F("pair_includemargin") = pair_includemargin;
   M.F("pair_friction") = pair_friction; M.F("pair_solref") = pair_solref; M.F("pair_solimp") = pair_solimp;
   M.F("qpos0") = qpos0;
+  M.set_int("ncam", (int)B.cam_bodyid.size());
+  M.I("cam_bodyid") = B.cam_bodyid; M.I("cam_mode") = B.cam_mode;
+  M.F("cam_pos") = B.cam_pos; M.F("cam_quat") = B.cam_quat; M.F("cam_fovy") = B.cam_fovy;
+  M.names[MJB_OBJ_CAMERA] = B.cam_name;
   M.names[MJB_OBJ_BODY] = B.body_name; M.names[MJB_OBJ_JOINT] = B.jnt_name; M.names[MJB_OBJ_GEOM] = B.geom_name;
   M.names[MJB_OBJ_SITE] = B.site_name; M.names[MJB_OBJ_SENSOR] = B.sensor_name; M.names[MJB_OBJ_ACTUATOR] = B.act_name;
 

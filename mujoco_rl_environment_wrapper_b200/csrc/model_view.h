@@ -44,6 +44,10 @@ struct ModelView {
   const int32_t *pair_geom1, *pair_geom2, *pair_condim;
   const double *pair_margin, *pair_includemargin, *pair_friction, *pair_solref, *pair_solimp;
   const double* qpos0;
+  // cameras (optional in older blobs)
+  int ncam = 0;
+  const int32_t *cam_bodyid = nullptr, *cam_mode = nullptr;
+  const double *cam_pos = nullptr, *cam_quat = nullptr, *cam_fovy = nullptr;
 
   const int32_t* I(const char* n, bool required = true) const {
     int c;
@@ -99,6 +103,11 @@ struct ModelView {
     pair_margin = F("pair_margin"); pair_includemargin = F("pair_includemargin");
     pair_friction = F("pair_friction"); pair_solref = F("pair_solref"); pair_solimp = F("pair_solimp");
     qpos0 = F("qpos0");
+    if (const int32_t* nc = I("ncam", false)) {
+      ncam = nc[0];
+      cam_bodyid = I("cam_bodyid"); cam_mode = I("cam_mode");
+      cam_pos = F("cam_pos"); cam_quat = F("cam_quat"); cam_fovy = F("cam_fovy");
+    }
   }
 };
 

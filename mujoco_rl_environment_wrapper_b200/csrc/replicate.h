@@ -28,7 +28,7 @@ inline void replicate_model(const HostModel& src, int K, HostModel& dst) {
     const bool is_int = src.i32.count(name) > 0;
     // scalars
     if (name == "nq" || name == "nv" || name == "nu" || name == "njnt" || name == "ngeom" || name == "nsite" ||
-        name == "nsensor" || name == "nsensordata" || name == "npair" || name == "ntree") {
+        name == "nsensor" || name == "nsensordata" || name == "npair" || name == "ntree" || name == "ncam") {
       dst.set_int(name, src.get_int(name) * K);
       continue;
     }
@@ -49,7 +49,7 @@ inline void replicate_model(const HostModel& src, int K, HostModel& dst) {
         for (size_t i = i0; i < v.size(); i++) {
           int x = v[i];
           if (name == "body_parentid" || name == "body_rootid" || name == "body_weldid" || name == "jnt_bodyid" ||
-              name == "dof_bodyid" || name == "geom_bodyid" || name == "site_bodyid") x = bmap(x, c);
+              name == "dof_bodyid" || name == "geom_bodyid" || name == "site_bodyid" || name == "cam_bodyid") x = bmap(x, c);
           else if (name == "body_jntadr" || name == "dof_jntid" || name == "actuator_trnid") x = off(x, c * njnt);
           else if (name == "body_dofadr" || name == "jnt_dofadr" || name == "dof_parentid") x = off(x, c * nv);
           else if (name == "body_geomadr" || name == "pair_geom1" || name == "pair_geom2") x = off(x, c * ngeom);

@@ -67,7 +67,8 @@ class MuJoCoRL:
         self.reward_functions = list(config_dict.get("rewardFunctions", []))
         self.done_functions = list(config_dict.get("doneFunctions", []))
         dynamics_classes = list(config_dict.get("environmentDynamics", []))
-        self.agent_cameras = config_dict.get("agentCameras", False)  # accepted, cameras are not observations
+        self.agent_cameras = config_dict.get("agentCameras", False)
+        self.sensor_resolution = tuple(config_dict.get("sensorResolution", (64, 64)))
         self.num_envs = int(config_dict.get("num_envs", 1))
         self.seed = int(config_dict.get("seed", 1234))
         dev = config_dict.get("device", None)
@@ -464,6 +465,38 @@ class MuJoCoRL:
         oi = self.agents_observation_index[agent]
         o = torch.cat([b.sensordata[:, oi["sensors"]], b.qpos[:, oi["qpos"]], b.qvel[:, oi["qvel"]]], dim=1)
         return self._out(o)
+
+    def get_camera_data(self, cam_object):
+        """mujoco_parent.py:540-556: images of all cameras of an agent ([N, n_cams, H, W, 3] u8), or of one named
+        camera ([N, H, W, 3]); num_envs = 1 returns the reference's numpy shapes.  Rows are bottom-up, as the
+        reference's glReadPixels buffer.  Needs "agentCameras": True, like the reference."""
+        if not self.agent_cameras:
+            raise Exception("get_camera_data needs config 'agentCameras': True")
+        w, h = self.sensor_resolution
+        if cam_object in self._tables.rgb_sensors:
+            names, squeeze = self._tables.rgb_sensors[cam_object], False
+        else:
+            names, squeeze = [cam_object], True
+        ids = []
+        for name in names:
+            cid = self.model.name2id(L.OBJ_CAMERA, name)
+            if cid < 0:
+                raise KeyError(f"Invalid name '{name}'. Valid names: "
+                               f"{[n for v in self._tables.rgb_sensors.values() for n in v]}")
+            ids.append(cid)
+        if not ids:
+            img = torch.zeros((self.num_envs, 0, h, w, 3), dtype=torch.uint8, device=self.device)
+        elif len(self._levels) == 1:
+            img = self._batch.render(ids, w, h)
+        else:   # every level renders all envs' qpos with its own geometry / colours; keep each env's own level
+            img = self._levels[0]["batch"].render(ids, w, h)
+            for lid, lv in enumerate(self._levels[1:], 1):
+                sel = self.level_id == lid
+                if bool(sel.any()):
+                    img[sel] = lv["batch"].render(ids, w, h)[sel]
+        if squeeze:
+            img = img[:, 0]
+        return img if self.num_envs > 1 else img[0].cpu().numpy()
 
     def _position(self, name_or_xyz):
         if isinstance(name_or_xyz, str):

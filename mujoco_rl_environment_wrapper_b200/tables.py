@@ -93,6 +93,7 @@ class Tables:
                 adr += SENSOR_DIM[kind]
         self.agents_observation_index, self.agents_action_index = {}, {}
         self.obs_space, self.act_space, self.agent_body = {}, {}, {}
+        self.rgb_sensors = {}   # agent -> names of the cameras in its subtree (mujoco_parent.py:505-516)
         motors = []
         act = self.root.find("actuator")
         if act is not None:
@@ -100,6 +101,7 @@ class Tables:
         for agent in agents:
             body = find_body(self.root, agent)
             self.agent_body[agent] = model.name2id(L.OBJ_BODY, agent)
+            self.rgb_sensors[agent] = [c.get("name") for c in _subtree_elems(body, "camera")]
             sites = {s.get("name") for s in _subtree_elems(body, "site")}
             mine = [s for s in self.sensors if s["site"] in sites]
             s_idx = [i for s in mine for i in s["indices"]]

@@ -1053,6 +1053,58 @@ int orc_contact(void* p, int i, int* geom, double* dist, double* pos, double* fr
   if (frame) for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) frame[3 * r + k] = c.frame[r][k];
   return 0;
 }
+// Agent camera `cam` of the current kinematic state (call after orc_forward / orc_kinematics): the image formation
+// documented in csrc/render_kernel.cuh, restated in fp64.  Reference: get_camera_data (mujoco_parent.py:518-556)
+// renders with MuJoCo's OpenGL pipeline, which cannot run here -> image parity with the reference is UNPINNED;
+// this function pins the CUDA raycaster.  out: u8 [height, width, 3], rows bottom-up.
+int orc_render(void* p, int cam, int width, int height, uint8_t* out) {
+  Sim* s = (Sim*)p;
+  const ModelView& m = *s->m;
+  if (cam < 0 || cam >= m.ncam || m.cam_mode[cam] != 0) return -1;
+  kinematics(*s);
+  const int b = m.cam_bodyid[cam];
+  V3 o = s->kin.xpos[b] + mulv(s->kin.xmat[b], V3(m.cam_pos[3 * cam], m.cam_pos[3 * cam + 1], m.cam_pos[3 * cam + 2]));
+  M3 R = q2m(qmul(s->kin.xquat[b], Quat{m.cam_quat[4 * cam], m.cam_quat[4 * cam + 1], m.cam_quat[4 * cam + 2], m.cam_quat[4 * cam + 3]}));
+  const double th = std::tan(0.5 * m.cam_fovy[cam] * 3.14159265358979323846 / 180.0), aspect = (double)width / height;
+  const double ambient = 0.4, diffuse = 0.6;
+  for (int iy = 0; iy < height; iy++)
+    for (int ix = 0; ix < width; ix++) {
+      V3 dl(((ix + 0.5) / width * 2 - 1) * th * aspect, ((iy + 0.5) / height * 2 - 1) * th, -1.0);
+      V3 d = mulv(R, normalized(dl));
+      double best = 1e300;
+      int bi = -1;
+      for (int g = 0; g < m.ngeom; g++) {
+        if (m.geom_rgba[4 * g + 3] <= 0) continue;
+        double t = ray_geom(gpos(*s, g), gmat(*s, g), &m.geom_size[3 * g], o, d, m.geom_type[g]);
+        if (t >= 0 && t < best) { best = t; bi = g; }
+      }
+      uint8_t* px = out + ((size_t)iy * width + ix) * 3;
+      if (bi < 0) { px[0] = px[1] = px[2] = 0; continue; }
+      V3 hit = o + d * best, gp = gpos(*s, bi);
+      M3 G = gmat(*s, bi);
+      const double* sz = &m.geom_size[3 * bi];
+      double nd;
+      int type = m.geom_type[bi];
+      if (type == MJB_GEOM_PLANE) nd = std::fabs(dot(V3(G(0, 2), G(1, 2), G(2, 2)), d));
+      else if (type == MJB_GEOM_SPHERE) nd = std::fabs(dot(normalized(hit - gp), d));
+      else {
+        V3 lp = mulTv(G, hit - gp), ld = mulTv(G, d);
+        if (type == MJB_GEOM_CAPSULE) {
+          V3 n(lp.x, lp.y, lp.z - std::min(std::max(lp.z, -sz[1]), sz[1]));
+          nd = std::fabs(dot(normalized(n), ld));
+        } else {
+          double ax = std::fabs(lp.x) / sz[0], ay = std::fabs(lp.y) / sz[1], az = std::fabs(lp.z) / sz[2];
+          nd = (ax >= ay && ax >= az) ? std::fabs(ld.x) : (ay >= az ? std::fabs(ld.y) : std::fabs(ld.z));
+        }
+      }
+      double I = ambient + diffuse * std::min(nd, 1.0);
+      for (int c = 0; c < 3; c++) {
+        double col = std::min(1.0, std::max(0.0, m.geom_rgba[4 * bi + c]));
+        px[c] = (uint8_t)(col * I * 255.0 + 0.5);
+      }
+    }
+  return 0;
+}
 // total mechanical energy (kinetic + gravitational potential), for the analytic tests
 double orc_energy(void* p) {
   Sim* s = (Sim*)p;

@@ -51,6 +51,7 @@ def _lib():
         lib.orc_contact.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]
+        lib.orc_render.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -125,6 +126,13 @@ class OracleSim:
 
     def energy(self):
         return self._lib.orc_energy(self._h)
+
+    def render(self, cam, width=64, height=64):
+        """u8 [height, width, 3] image of fixed camera `cam` at the current qpos (rows bottom-up)"""
+        out = np.zeros((height, width, 3), np.uint8)
+        if self._lib.orc_render(self._h, cam, width, height, out.ctypes.data) != 0:
+            raise ValueError(f"camera {cam} cannot be rendered")
+        return out
 
     def contact(self, i):
         g = (ctypes.c_int * 2)()
