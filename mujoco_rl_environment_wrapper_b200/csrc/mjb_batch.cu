@@ -445,7 +445,8 @@ int mjb_render(mjb_batch* b, const int32_t* cam_ids, int32_t ncams, int32_t widt
   }
   CUDA_TRY(cudaSetDevice(b->device));
   const mjb::DevModel& dm = b->rimg.dm;
-  const size_t smem = ((size_t)dm.image_words + dm.env_words + rh.words + (size_t)dm.ngeom * mjb::GL_STRIDE + 12 * RENDER_MAX_CAMS) * 4;
+  const size_t smem = ((size_t)dm.image_words + dm.env_words + rh.words + (size_t)dm.ngeom * mjb::GL_STRIDE + 12 * RENDER_MAX_CAMS) * 4 +
+                      (size_t)RENDER_TILE_BATCH * ((dm.ngeom + 2) & ~1) * 2;
   if (!b->d_rimage) {
     CUDA_TRY(cudaMalloc(&b->d_rimage, b->rimg.words.size() * 4));
     CUDA_TRY(cudaMalloc(&b->d_rtab, b->rimg.render.size() * 4));

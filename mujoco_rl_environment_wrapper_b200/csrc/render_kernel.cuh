@@ -9,8 +9,9 @@
 // the CPU oracle restates exactly this image formation in fp64).
 //
 // One CTA per env: warp 0 redoes the kinematics pass from the env's qpos, the CTA flattens the geoms into a
-// broadcast-friendly list in shared memory, then every thread shades groups of 4 neighbouring pixels and
-// writes them as three 32-bit words (coalesced 384 B per warp).
+// broadcast-friendly list in shared memory and culls them per 16 x 8 pixel tile (bounding sphere against the
+// tile's view cone, conservative, so the image is unchanged), then one warp shades one tile: every lane takes
+// 4 neighbouring pixels, walks the tile's short geom list (warp-uniform) and writes three 32-bit words.
 #pragma once
 #include "step_kernel.cuh"
 
@@ -22,22 +23,42 @@ namespace mjb {
 
 struct RenderCams { int n; int id[RENDER_MAX_CAMS]; };
 
+// ray / box by slabs: the same first non-negative face crossing ray_geom enumerates face by face, in a third of
+// the instructions (boxes — arena walls, targets — are what most camera rays test)
+MJB_DEV float ray_box_slabs(f3 pos, const float* R, const float* size, f3 pnt, f3 vec) {
+  f3 lp = mulTv(R, pnt - pos), lv = mulTv(R, vec);
+  float tn = -MJB_BIG, tf = MJB_BIG;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float p = comp(lp, a), v = comp(lv, a), s = size[a];
+    if (fabsf(v) < MJB_MINVAL) {
+      if (fabsf(p) > s) return -1.f;
+    } else {
+      const float inv = 1.f / v, t1 = (-s - p) * inv, t2 = (s - p) * inv;
+      tn = fmaxf(tn, fminf(t1, t2));
+      tf = fminf(tf, fmaxf(t1, t2));
+    }
+  }
+  if (tn > tf || tf < 0.f) return -1.f;
+  return tn >= 0.f ? tn : tf;
+}
+
 // colour of the first geom along the ray (o, unit d); packed 0x00BBGGRR
-MJB_DEV uint32_t shade_ray(const float* GL, int ngeom, f3 o, f3 d) {
+MJB_DEV_NOINLINE uint32_t shade_ray(const float* GL, const uint16_t* list, int nlist, f3 o, f3 d) {
   float best = MJB_BIG;
   int bi = -1;
   MJB_NOUNROLL
-  for (int g = 0; g < ngeom; g++) {
+  for (int i = 0; i < nlist; i++) {   // ascending geom ids: ties resolve as in the oracle's loop
+    const int g = list[i];
     const float* G = GL + g * GL_STRIDE;
     const int type = __float_as_int(G[GL_TYPE]);
-    if (type < 0) continue;  // invisible (alpha == 0)
     f3 pos = ld3(G + GL_POS);
     if (type != MJB_GEOM_PLANE) {  // bounding sphere first
       f3 oc = pos - o;
       float tca = dot(oc, d), l2 = dot(oc, oc), rb = G[GL_RBOUND];
       if (l2 - tca * tca > rb * rb || (tca < 0.f && l2 > rb * rb) || tca - rb > best) continue;
     }
-    float t = ray_geom(pos, G + GL_MAT, G + GL_SIZE, o, d, type);
+    float t = type == MJB_GEOM_BOX ? ray_box_slabs(pos, G + GL_MAT, G + GL_SIZE, o, d) : ray_geom(pos, G + GL_MAT, G + GL_SIZE, o, d, type);
     if (t >= 0.f && t < best) { best = t; bi = g; }
   }
   if (bi < 0) return 0u;
@@ -68,6 +89,17 @@ MJB_DEV uint32_t shade_ray(const float* GL, int ngeom, f3 o, f3 d) {
 }
 
 #if !defined(MJB_HOST_EMU)
+#define RENDER_TILE_W 16
+#define RENDER_TILE_H 8
+#define RENDER_TILE_BATCH 128   // tiles whose geom lists are resident at once
+
+// direction of the ray through image-plane point (fx, fy) in pixels (pixel centres are at +0.5)
+MJB_DEV f3 pixel_dir(const float* cw, float th, float fx, float fy, int width, int height) {
+  float u = (fx / width * 2.f - 1.f) * th * ((float)width / (float)height), v = (fy / height * 2.f - 1.f) * th;
+  f3 dl = mk3(u, v, -1.f);   // camera frame: looks along -z, +y up
+  return mulv(cw + 3, dl * MJB_RSQRT(dot(dl, dl)));
+}
+
 // out: u8 [num_envs, cams.n, height, width, 3]
 __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image,
                                                 const RenderHdr rh, const uint32_t* __restrict__ rtab,
@@ -79,14 +111,17 @@ __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DevModel
   uint32_t* tab = reinterpret_cast<uint32_t*>(scratch + dm.env_words);
   float* GL = reinterpret_cast<float*>(tab + rh.words);
   float* CW = GL + dm.ngeom * GL_STRIDE;   // per requested camera: world pos[3], rotation[9]
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int lstride = (dm.ngeom + 2) & ~1;  // u16 per tile: count, then geom ids
+  uint16_t* TL = reinterpret_cast<uint16_t*>(CW + 12 * RENDER_MAX_CAMS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   for (int i = tid; i < dm.image_words; i += blockDim.x) img[i] = image[i];
   for (int i = tid; i < rh.words; i += blockDim.x) tab[i] = rtab[i];
   __syncthreads();
   Ctx c{&dm, img, scratch, lane, nullptr, 0, 0};
   const float* rgba = reinterpret_cast<const float*>(tab + rh.off_rgba);
-  const int px = (width & 3) ? 1 : 4;            // pixels per work item
-  const int items_row = width / px, items_cam = items_row * height, items = items_cam * cams.n;
+  const int tiles_x = (width + RENDER_TILE_W - 1) / RENDER_TILE_W, tiles_y = (height + RENDER_TILE_H - 1) / RENDER_TILE_H;
+  const int tiles_cam = tiles_x * tiles_y, ntiles = tiles_cam * cams.n;
+  const bool words = (width & 3) == 0;   // 4-pixel groups never straddle the right edge: 12-byte stores
   for (int env = blockIdx.x; env < num_envs; env += gridDim.x) {
     if (tid < 32) {
       float* qpos = SF(qpos);
@@ -101,7 +136,7 @@ __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DevModel
       st3(G + GL_POS, w.pos);
       for (int i = 0; i < 9; i++) G[GL_MAT + i] = w.mat[i];
       for (int i = 0; i < 3; i++) { G[GL_SIZE + i] = w.size[i]; G[GL_RGB + i] = rgba[4 * g + i]; }
-      G[GL_TYPE] = __int_as_float(rgba[4 * g + 3] > 0.f ? w.type : -1);
+      G[GL_TYPE] = __int_as_float(rgba[4 * g + 3] > 0.f ? w.type : -1);   // alpha == 0: invisible
       G[GL_RBOUND] = CF(geom_rbound)[g];
     }
     for (int k = tid; k < cams.n; k += blockDim.x) {
@@ -115,32 +150,74 @@ __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DevModel
       q2m(q, CW + 12 * k + 3);
     }
     __syncthreads();
-    for (int it = tid; it < items; it += blockDim.x) {
-      const int k = it / items_cam, r = it - k * items_cam, iy = r / items_row, ix0 = (r - iy * items_row) * px;
-      const float* cw = CW + 12 * k;
-      const float th = reinterpret_cast<const float*>(tab + rh.off_cam + cams.id[k] * CAM_STRIDE)[CAM_TANHALF];
-      const f3 o = ld3(cw);
-      const float v = ((iy + 0.5f) / height * 2.f - 1.f) * th;
-      uint32_t col[4];
+    for (int t0 = 0; t0 < ntiles; t0 += RENDER_TILE_BATCH) {
+      const int nb = min(RENDER_TILE_BATCH, ntiles - t0);
+      // (1) per tile: the geoms whose bounding sphere reaches into the tile's view cone.  f(p) = |p_perp| cos(a)
+      //     - p_axis sin(a) is 1-Lipschitz and <= 0 inside the cone, so f(centre) > radius proves "not visible".
+      for (int t = warp; t < nb; t += nwarps) {   // a warp per tile, a lane per geom, ballot-compacted in id order
+        const int tile = t0 + t, k = tile / tiles_cam, r = tile - k * tiles_cam, ty = r / tiles_x, tx = r - ty * tiles_x;
+        const float* cw = CW + 12 * k;
+        const float th = reinterpret_cast<const float*>(tab + rh.off_cam + cams.id[k] * CAM_STRIDE)[CAM_TANHALF];
+        const float x0 = tx * RENDER_TILE_W, y0 = ty * RENDER_TILE_H;
+        const float x1 = fminf(x0 + RENDER_TILE_W, (float)width), y1 = fminf(y0 + RENDER_TILE_H, (float)height);
+        const f3 o = ld3(cw), axis = pixel_dir(cw, th, 0.5f * (x0 + x1), 0.5f * (y0 + y1), width, height);
+        // lanes 0..3 take one corner each
+        float ca = dot(axis, pixel_dir(cw, th, (lane & 1) ? x1 : x0, (lane & 2) ? y1 : y0, width, height));
+        ca = fminf(ca, __shfl_xor_sync(0xffffffffu, ca, 1));
+        ca = fminf(ca, __shfl_xor_sync(0xffffffffu, ca, 2));
+        ca = fmaxf(__shfl_sync(0xffffffffu, ca, 0) - 1e-4f, 0.f);   // widen by rounding slack
+        const float sa = sqrtf(fmaxf(1.f - ca * ca, 0.f));
+        uint16_t* L = TL + t * lstride;
+        int n = 0;
+        MJB_NOUNROLL
+        for (int g0 = 0; g0 < dm.ngeom; g0 += 32) {
+          const int g = g0 + lane;
+          bool keep = false;
+          if (g < dm.ngeom) {
+            const float* G = GL + g * GL_STRIDE;
+            const int type = __float_as_int(G[GL_TYPE]);
+            keep = type >= 0;
+            if (keep && type != MJB_GEOM_PLANE) {
+              f3 v = ld3(G + GL_POS) - o;
+              float pa = dot(v, axis), pp = sqrtf(fmaxf(dot(v, v) - pa * pa, 0.f));
+              keep = pp * ca - pa * sa <= G[GL_RBOUND] * 1.0001f + 1e-5f;
+            }
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, keep);
+          if (keep) L[1 + n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)g;
+          n += __popc(m);
+        }
+        if (lane == 0) L[0] = (uint16_t)n;
+      }
+      __syncthreads();
+      // (2) one warp per tile, one lane per 4-pixel group (4 groups per tile row)
+      for (int t = warp; t < nb; t += nwarps) {
+        const int tile = t0 + t, k = tile / tiles_cam, r = tile - k * tiles_cam, ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int iy = ty * RENDER_TILE_H + (lane >> 2), ix0 = tx * RENDER_TILE_W + (lane & 3) * 4;
+        if (iy >= height || ix0 >= width) continue;
+        const float* cw = CW + 12 * k;
+        const float th = reinterpret_cast<const float*>(tab + rh.off_cam + cams.id[k] * CAM_STRIDE)[CAM_TANHALF];
+        const f3 o = ld3(cw);
+        const uint16_t* L = TL + t * lstride;
+        const int nl = L[0];
+        uint32_t col[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (j >= px) break;
-        float u = ((ix0 + j + 0.5f) / width * 2.f - 1.f) * th * ((float)width / (float)height);
-        f3 dl = mk3(u, v, -1.f);   // camera frame: looks along -z, +y up
-        f3 d = mulv(cw + 3, dl * MJB_RSQRT(dot(dl, dl)));
-        col[j] = shade_ray(GL, dm.ngeom, o, d);
+        for (int j = 0; j < 4; j++)
+          col[j] = (ix0 + j < width) ? shade_ray(GL, L + 1, nl, o, pixel_dir(cw, th, ix0 + j + 0.5f, iy + 0.5f, width, height)) : 0u;
+        uint8_t* dst = out + ((((size_t)env * cams.n + k) * height + iy) * width + ix0) * 3;
+        if (words) {  // 12 bytes = three aligned words
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+          d32[0] = col[0] | (col[1] << 24);
+          d32[1] = (col[1] >> 8) | (col[2] << 16);
+          d32[2] = (col[2] >> 16) | (col[3] << 8);
+        } else {
+          for (int j = 0; j < 4 && ix0 + j < width; j++) {
+            dst[3 * j] = col[j] & 0xff; dst[3 * j + 1] = (col[j] >> 8) & 0xff; dst[3 * j + 2] = (col[j] >> 16) & 0xff;
+          }
+        }
       }
-      uint8_t* dst = out + ((((size_t)env * cams.n + k) * height + iy) * width + ix0) * 3;
-      if (px == 4) {  // 12 bytes = three aligned words
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        d32[0] = col[0] | (col[1] << 24);
-        d32[1] = (col[1] >> 8) | (col[2] << 16);
-        d32[2] = (col[2] >> 16) | (col[3] << 8);
-      } else {
-        dst[0] = col[0] & 0xff; dst[1] = (col[0] >> 8) & 0xff; dst[2] = (col[0] >> 16) & 0xff;
-      }
+      __syncthreads();   // the tile lists (and, after the last batch, the scratch) are reused
     }
-    __syncthreads();   // the scratch is reused by the next env
   }
 }
 #endif
