@@ -51,7 +51,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <bool PHYS, bool PACKED>
 __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
                       int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env,
-                      int lockstep_groups, const int* __restrict__ env_order, int active) {
+                      int lockstep_groups, const int* __restrict__ env_order, int active, int env_base) {
   const int lockstep = lockstep_groups & 0xff, groups = lockstep_groups >> 8;
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
       // (a masked reset lets warps skip their env, so intra-step alignment is off for it)
       c.cta_threads = (mask == nullptr ? 32 : 0) * (busy > warps ? warps : (busy < 0 ? 0 : busy));
     }
-    if (env < nvirt) run_env<PHYS, PACKED>(c, B, env_order ? env_order[env] : env, num_envs, mode, skip_frames, mask);
+    if (env < nvirt) run_env<PHYS, PACKED>(c, B, env_order ? env_order[env] : env + env_base, num_envs, mode, skip_frames, mask);
     if (lockstep) {
       if (groups > 1) {
         // the env-warps re-align in `groups` independent sets: fewer warps wait on the slowest env of a round,
@@ -122,6 +122,9 @@ struct mjb_batch {
   int num_envs = 0, device = 0, warps = 0, grid = 0;
   size_t smem_bytes = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // host-buffer step: second half of the envs (copy / compute overlap)
+  cudaEvent_t ev_fork = nullptr, ev_k0 = nullptr, ev_join = nullptr;
+  int host_split = 1;                        // MJB_HOST_SPLIT: 1 = pipeline the host-buffer step in two halves
   uint32_t* d_image = nullptr;
   int* d_next = nullptr;   // ring of work counters, one per in-flight launch
   int next_slot = 0;
@@ -151,36 +154,40 @@ namespace {
     }                                                                                       \
   } while (0)
 
-int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask) {
+// `base` / `count` (in envs, multiples of the pack factor) restrict the launch to a contiguous env range
+int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStream_t stream = nullptr, int base = 0, int count = -1) {
   if (b->subset && b->subset_count == 0) return MJB_OK;   // no env on this level right now
+  if (!stream) stream = b->stream;
+  const int active = b->subset ? b->subset_count : (count >= 0 ? count : b->num_envs);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (b->timing) {
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    CUDA_TRY(cudaEventRecord(e0, b->stream));
+    CUDA_TRY(cudaEventRecord(e0, stream));
   }
   // the first grid*warps envs are taken statically; the counter hands out the rest
   int first = b->grid * b->warps;
   int* counter = b->d_next + b->next_slot;
   b->next_slot = (b->next_slot + 1) % 64;
   if (b->lockstep == 0)  // only the dynamic scheduler consumes the counter
-    CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, stream));
   (void)first;
   if (mode == mjb::MODE_STEP && b->has_lite) {
     // no physics in the step: many small envs per SM, rounds aligned the same way
-    mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, b->stream>>>(b->lite.dm, b->d_image, b->B, b->num_envs, mode,
-                                                                                      skip_frames, mask, counter, 2, b->subset,
-                                                                                      b->subset ? b->subset_count : b->num_envs);
+    mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, stream>>>(b->lite.dm, b->d_image, b->B, b->num_envs, mode,
+                                                                                   skip_frames, mask, counter, 2, b->subset, active, base);
   } else {
     auto kern = b->img.dm.pack > 1 ? mjb::k_env<true, true> : mjb::k_env<true, false>;
-    kern<<<b->grid, b->warps * 32, b->smem_bytes, b->stream>>>(b->img.dm, b->d_image, b->B, b->num_envs, mode, skip_frames, mask,
-                                                                counter, b->lockstep | (b->groups << 8),
-                                                                b->subset ? b->subset : ((b->lockstep && b->img.dm.pack == 1) ? b->env_order : nullptr),
-                                                                b->subset ? b->subset_count : b->num_envs);
+    const int pack = b->img.dm.pack;
+    const bool ranged = count >= 0 && !b->subset;   // a range launch walks env ids directly
+    const int need = ((active + pack - 1) / pack + b->warps - 1) / b->warps;
+    kern<<<std::min(b->grid, std::max(1, need)), b->warps * 32, b->smem_bytes, stream>>>(
+        b->img.dm, b->d_image, b->B, b->num_envs, mode, skip_frames, mask, counter, b->lockstep | (b->groups << 8),
+        b->subset ? b->subset : ((b->lockstep && pack == 1 && !ranged) ? b->env_order : nullptr), active, base / pack);
   }
   CUDA_TRY(cudaGetLastError());
   if (b->timing) {
-    CUDA_TRY(cudaEventRecord(e1, b->stream));
+    CUDA_TRY(cudaEventRecord(e1, stream));
     b->events.emplace_back(e0, e1);
   }
   b->launches++;
@@ -295,10 +302,18 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     return fail(MJB_ERR_CUDA);
   }
   b->h_first[0] = b->grid * b->warps;
+  b->host_split = mjb::env_int("MJB_HOST_SPLIT", 1);
+  if (cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->ev_k0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    mjb::set_error("mjb_batch_create: stream / event creation failed");
+    return fail(MJB_ERR_CUDA);
+  }
   b->lockstep = mjb::env_int("MJB_LOCKSTEP", 2);
   b->groups = mjb::env_int("MJB_GROUPS", 1);
   if (b->groups < 1 || b->groups > 8 || b->lockstep != 2) b->groups = 1;
-  const int A = dm.n_agents;
+  const int A = dm.a1;
   if (cudaMallocHost(&b->h_act, sizeof(float) * (size_t)num_envs * A * dm.act_stride + 16) != cudaSuccess ||
       cudaMallocHost(&b->h_obs, sizeof(float) * (size_t)num_envs * A * dm.obs_stride + 16) != cudaSuccess ||
       cudaMallocHost(&b->h_rew, sizeof(float) * (size_t)num_envs * A + 16) != cudaSuccess ||
@@ -315,6 +330,8 @@ void mjb_batch_destroy(mjb_batch* b) {
   if (!b) return;
   for (auto& ev : b->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (b->d_image) cudaFree(b->d_image);
+  if (b->stream2) cudaStreamDestroy(b->stream2);
+  for (cudaEvent_t e : {b->ev_fork, b->ev_k0, b->ev_join}) if (e) cudaEventDestroy(e);
   if (b->d_rimage) cudaFree(b->d_rimage);
   if (b->d_rtab) cudaFree(b->d_rtab);
   if (b->d_next) cudaFree(b->d_next);
@@ -352,7 +369,7 @@ int mjb_sync(mjb_batch* b) {
 int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward, uint8_t* term, uint8_t* trunc) {
   if (!b || !actions || !obs || !reward || !term || !trunc) { mjb::set_error("mjb_step_host: null argument"); return MJB_ERR_ARG; }
   const mjb::DevModel& dm = b->img.dm;
-  const size_t N = b->num_envs, A = dm.n_agents;
+  const size_t N = b->num_envs, A = dm.a1;   // agents of ONE real env (the image may pack several envs per warp)
   const size_t nb_act = sizeof(float) * N * A * dm.act_stride, nb_obs = sizeof(float) * N * A * dm.obs_stride;
   const size_t nb_rew = sizeof(float) * N * A, nb_flag = N * (A + 1);
   // page-locked caller buffers are copied directly; pageable ones go through the pinned staging area
@@ -368,9 +385,6 @@ int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward,
   } else {
     memcpy(b->h_act, actions, nb_act);
   }
-  CUDA_TRY(cudaMemcpyAsync(b->B.actions, direct ? actions : b->h_act, nb_act, cudaMemcpyHostToDevice, b->stream));
-  int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr);
-  if (rc != MJB_OK) return rc;
   // when the four result arrays sit back to back (16-byte aligned) on both sides, one copy returns them all
   auto r16 = [](size_t n) { return (n + 15) / 16 * 16; };
   const char *d0 = (const char*)b->B.obs, *h0 = (const char*)obs;
@@ -378,6 +392,34 @@ int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward,
                           (const char*)b->B.term == d0 + r16(nb_obs) + r16(nb_rew) && (const char*)term == h0 + r16(nb_obs) + r16(nb_rew) &&
                           (const char*)b->B.trunc == d0 + r16(nb_obs) + r16(nb_rew) + r16(nb_flag) &&
                           (const char*)trunc == h0 + r16(nb_obs) + r16(nb_rew) + r16(nb_flag);
+  // Two halves on two streams: the second half's actions go up while the first half computes, and the first
+  // half's observations come down while the second half computes.  Same results (envs are independent).
+  const int pack = dm.pack;
+  int half = (int)((N / 2 + pack - 1) / pack * pack);
+  if (b->host_split && packed_out && !b->subset && b->lockstep != 0 && N >= (size_t)(4 * b->warps) && half > 0 && (size_t)half < N) {
+    const size_t act_row = sizeof(float) * A * dm.act_stride, obs_row = sizeof(float) * A * dm.obs_stride;
+    CUDA_TRY(cudaEventRecord(b->ev_fork, b->stream));
+    CUDA_TRY(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
+    CUDA_TRY(cudaMemcpyAsync(b->B.actions, actions, act_row * half, cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaMemcpyAsync((char*)b->B.actions + act_row * half, (const char*)actions + act_row * half, act_row * (N - half),
+                             cudaMemcpyHostToDevice, b->stream2));
+    int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr, b->stream, 0, half);
+    if (rc != MJB_OK) return rc;
+    CUDA_TRY(cudaEventRecord(b->ev_k0, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(obs, b->B.obs, obs_row * half, cudaMemcpyDeviceToHost, b->stream));
+    rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr, b->stream2, half, (int)N - half);
+    if (rc != MJB_OK) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(b->stream2, b->ev_k0, 0));   // the tail copy also carries the first half's rewards / flags
+    CUDA_TRY(cudaMemcpyAsync((char*)obs + obs_row * half, (const char*)b->B.obs + obs_row * half,
+                             (r16(nb_obs) - obs_row * half) + r16(nb_rew) + r16(nb_flag) + nb_flag, cudaMemcpyDeviceToHost, b->stream2));
+    CUDA_TRY(cudaEventRecord(b->ev_join, b->stream2));
+    CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return MJB_OK;
+  }
+  CUDA_TRY(cudaMemcpyAsync(b->B.actions, direct ? actions : b->h_act, nb_act, cudaMemcpyHostToDevice, b->stream));
+  int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr);
+  if (rc != MJB_OK) return rc;
   if (packed_out) {
     CUDA_TRY(cudaMemcpyAsync(obs, b->B.obs, r16(nb_obs) + r16(nb_rew) + r16(nb_flag) + nb_flag, cudaMemcpyDeviceToHost, b->stream));
   } else {

@@ -570,3 +570,41 @@ def test_level_variants_reject_structural_mismatch(tmp_path):
     with pytest.raises(Exception, match="structurally identical"):
         MuJoCoRL({"xmlPath": [os.path.join(lv, "two_ants.xml"), os.path.join(lv, "two_ants_touch.xml")],
                   "agents": ["sender", "receiver"], "num_envs": 4})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene_xml,agents,n,pinned,split", [
+    ("two_ants.xml", ["sender", "receiver"], 100, True, "1"), ("two_ants.xml", ["sender", "receiver"], 100, True, "0"),
+    ("two_ants.xml", ["sender", "receiver"], 37, False, "1"), ("one_ant_arena.xml", ["sender"], 101, True, "1"),
+    ("ant_rk4.xml", ["torso"], 64, True, "1")])
+def test_step_host_matches_device_step(monkeypatch, scene_xml, agents, n, pinned, split):
+    """mjb_step_host (host arrays in / out, two pipelined halves when the arrays are page-locked) returns exactly what
+    mjb_step leaves in the device buffers; also with several envs per warp (one_ant_arena) and a ragged split."""
+    import os
+    from mujoco_rl_environment_wrapper_b200 import plugins as P
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    monkeypatch.setenv("MJB_HOST_SPLIT", split)
+    lv = os.path.join(os.path.dirname(__file__), "levels")
+    cfg = {"xmlPath": os.path.join(lv, scene_xml), "agents": agents, "num_envs": n, "seed": 11}
+    if len(agents) == 2:
+        cfg.update(infoJson=os.path.join(lv, "info_2A.json"), environmentDynamics=[P.Language],
+                   rewardFunctions=[P.tag_distance_reward], doneFunctions=[P.distance_done])
+    if scene_xml == "ant_rk4.xml":
+        cfg.update(freeJoint=True, skipFrames=0, rewardFunctions=[P.ant_reward_function])   # the no-physics step kernel
+    dev, host = MuJoCoRL(cfg), MuJoCoRL(cfg)
+    dev.reset(); host.reset()
+    hb = host.batch
+    arrs = hb.host_arrays(pinned=pinned)
+    if not pinned:
+        arrs = tuple(np.array(a) for a in arrs)   # plain pageable numpy
+    h_act, h_obs, h_rew, h_term, h_trunc = arrs
+    for t in range(25):
+        a = dev.sample_actions()
+        assert torch.equal(a, host.sample_actions())
+        dev.batch.actions[:, :, :dev._act_dim] = a
+        dev.batch.step()
+        h_act[:, :, :dev._act_dim] = a.cpu().numpy()
+        hb.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
+        for name, got in (("obs", h_obs), ("reward", h_rew), ("term", h_term), ("trunc", h_trunc)):
+            assert np.array_equal(got, getattr(dev.batch, name).cpu().numpy()), (t, name)
+        assert torch.equal(hb.qpos, dev.batch.qpos)
