@@ -267,6 +267,19 @@ def run_ours(args):
             if tj.get("envs_per_gpu") == N:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         achieved = bytes_env * N / (kern_ms * 1e-3) / 1e9
+        # the bound that actually binds: warp-instruction issue.  Executed warp instructions per launch come from the
+        # committed ncu capture of this workload; the rate is live (this run's kernel time and SM clock).
+        issue = None
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("envs_per_gpu") == N and tj.get("warp_instructions"):
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965
+                peak_ips = sms * 4 * mhz * 1e6
+                ips = tj["warp_instructions"] / (kern_ms * 1e-3)
+                issue = {"warp_instructions_per_launch": tj["warp_instructions"], "achieved_ginst_s": ips / 1e9,
+                         "peak_ginst_s": peak_ips / 1e9, "frac": ips / peak_ips,
+                         "note": "4 issue slots per SM per cycle; instruction count from profiles/ (ncu), time and clock live"}
         agent_steps = N * A * world
         out = {
             "metric": "agent-steps/sec", "value": agent_steps / (step_ms * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
@@ -279,7 +292,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": which, "algorithmic_bytes_per_env_step": bytes_env, "kernel_ms": kern_ms_max,
-                         "note": "physics-on step is issue/latency bound (SURVEY 8d): see profiles/ for issue-slot and stall evidence"},
+                         "note": "physics-on step is issue/latency bound (SURVEY 8d): see profiles/ for issue-slot and stall evidence",
+                         "issue": issue},
             "clocks": clk,
             "episode_stats_allgather": allstats.cpu().tolist(),
         }
