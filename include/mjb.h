@@ -111,6 +111,9 @@ typedef struct mjb_env_spec {
   int32_t solver_iterations;          /* fixed Newton iteration count per substep (0 = library default) */
   int32_t ls_iterations;              /* fixed line-search iterations (0 = default) */
   int32_t flags;                      /* MJB_SPEC_* bits */
+  float reset_noise;                  /* 0 = every reset starts at qpos0 / zero velocity like the reference
+                                         (mujoco_parent.py:349); > 0: hinge / slide qpos and all qvel start at
+                                         +- reset_noise (uniform, counter-based stream) to decorrelate envs */
 } mjb_env_spec;
 
 /* mjb_env_spec.flags */

@@ -45,7 +45,7 @@ class EnvSpec(ctypes.Structure):
         ("n_targets", ctypes.c_int32),
         ("target_objtype", ctypes.c_int32 * MAX_TARGETS), ("target_objid", ctypes.c_int32 * MAX_TARGETS),
         ("seed", ctypes.c_uint64),
-        ("solver_iterations", ctypes.c_int32), ("ls_iterations", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("solver_iterations", ctypes.c_int32), ("ls_iterations", ctypes.c_int32), ("flags", ctypes.c_int32), ("reset_noise", ctypes.c_float),
     ]
 
 

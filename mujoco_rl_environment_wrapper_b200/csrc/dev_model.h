@@ -133,6 +133,8 @@ struct DevModel {
   float timestep, gravity[3];
   int solver_iterations, ls_iterations;
   float solver_tol;
+  float reset_noise;   // 0: resets start exactly at qpos0 (reference behaviour)
+  int njnt1;           // joints of one real env
   // env spec
   int n_agents, free_joint, skip_frames, max_steps, n_phys_act, act_dim;
   int obs_dim[8], obs_adr[9], agent_probe[8];

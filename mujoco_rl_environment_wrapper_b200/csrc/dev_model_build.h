@@ -90,6 +90,8 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   for (int i = 0; i < 3; i++) dm.gravity[i] = (float)m.gravity[i];
   dm.ldj = m.nv | 1;  // narrowed below to the widest contact dof mask
   dm.solver_iterations = spec.solver_iterations > 0 ? spec.solver_iterations : env_int("MJB_SOLVER_ITERS", 24);
+  dm.reset_noise = spec.reset_noise > 0 ? spec.reset_noise : 0.f;
+  dm.njnt1 = m.njnt / pack;
   dm.ls_iterations = spec.ls_iterations > 0 ? spec.ls_iterations : env_int("MJB_LS_ITERS", 12);
   {
     const char* ts = getenv("MJB_SOLVER_TOL");

@@ -208,6 +208,32 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
     split_copy(i, dm.ns1, K, k, j);
     sens[i] = (fresh(k) || !has(k)) ? 0.f : B.sensordata[(size_t)(e0 + k) * dm.sensor_stride + j];
   }
+  if (mode == MODE_RESET && dm.reset_noise > 0.f) {
+    // optional decorrelated starts (off by default: the reference always restarts at qpos0).  The draw is keyed by
+    // (seed, env, joint / dof) and by how the previous episode ended, so that it differs from reset to reset.
+    MJB_SYNC();
+    MJB_NOUNROLL
+    for (int j = lane; j < dm.njnt; j += 32) {
+      const int k = K == 1 ? 0 : j / dm.njnt1;
+      if (!fresh(k) || !has(k) || CI(jnt_type)[j] == MJB_JNT_FREE) continue;
+      const uint32_t env = (uint32_t)(e0 + k);
+      const uint32_t ep = (uint32_t)B.timestep[env] ^ MJB_F2U(B.qpos[(size_t)env * dm.qpos_stride]) ^
+                          (MJB_F2U(B.qvel[(size_t)env * dm.qvel_stride]) << 13);
+      const float u = (float)(draw_u32(dm.seed ^ 0x5eedc0deULL, env, 0x4000u + (uint32_t)(j - k * dm.njnt1), ep) >> 8) * (1.f / 16777216.f);
+      qpos[CI(jnt_qposadr)[j]] += dm.reset_noise * (2.f * u - 1.f);
+    }
+    MJB_NOUNROLL
+    for (int i = lane; i < dm.nv; i += 32) {
+      int k, j;
+      split_copy(i, dm.nv1, K, k, j);
+      if (!fresh(k) || !has(k)) continue;
+      const uint32_t env = (uint32_t)(e0 + k);
+      const uint32_t ep = (uint32_t)B.timestep[env] ^ MJB_F2U(B.qpos[(size_t)env * dm.qpos_stride]) ^
+                          (MJB_F2U(B.qvel[(size_t)env * dm.qvel_stride]) << 13);
+      const float u = (float)(draw_u32(dm.seed ^ 0x5eedc0deULL, env, 0x8000u + (uint32_t)j, ep) >> 8) * (1.f / 16777216.f);
+      qvel[i] = dm.reset_noise * (2.f * u - 1.f);
+    }
+  }
   // exported positions: virtual probe order is [agents of every copy ..., targets of every copy ...]
   auto probe_slot = [&](int p, int& k, int& p1) {
     if (K == 1) { k = 0; p1 = p; }

@@ -6,6 +6,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(MJB_HOST_EMU)
 #include "../../tests/emu/simt_emu.h"
@@ -20,6 +21,8 @@
 #define MJB_POPC(x) __builtin_popcount(x)
 #define MJB_FFS(x) __builtin_ffs(x)
 #define MJB_RSQRT(x) (1.0f / sqrtf(x))
+inline uint32_t mjb_f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
+#define MJB_F2U(x) mjb_f2u(x)
 #define MJB_CTA_SYNC(nthreads) ((void)0)
 #define MJB_CTA_ANY(nthreads, pred) (pred)
 #else
@@ -34,6 +37,7 @@
 #define MJB_POPC(x) __popc(x)
 #define MJB_FFS(x) __ffs(x)
 #define MJB_RSQRT(x) rsqrtf(x)
+#define MJB_F2U(x) __float_as_uint(x)
 // CTA-level alignment of the env-warps that are busy in this round (named barrier 1 with an explicit
 // thread count, so idle warps of a partial round do not take part).  nthreads == 0 disables it.
 __device__ __forceinline__ void mjb_cta_sync(int nthreads) {

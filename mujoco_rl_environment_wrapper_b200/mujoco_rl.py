@@ -71,6 +71,7 @@ class MuJoCoRL:
         self.sensor_resolution = tuple(config_dict.get("sensorResolution", (64, 64)))
         self.num_envs = int(config_dict.get("num_envs", 1))
         self.seed = int(config_dict.get("seed", 1234))
+        self.reset_noise = float(config_dict.get("resetNoise", 0.0))   # new, off: the reference restarts at qpos0
         dev = config_dict.get("device", None)
         if not torch.cuda.is_available():
             raise RuntimeError("MuJoCoRL (B200): no CUDA device available; this implementation has no CPU fallback")
@@ -307,6 +308,7 @@ class MuJoCoRL:
             spec.target_objtype[t], spec.target_objid[t] = ot, oid
             self._probe_names.append(name)
         spec.seed = self.seed
+        spec.reset_noise = float(self.reset_noise)
         self._ai = (ctypes.c_int32 * max(1, len(act_index)))(*act_index)
         self._oi = (ctypes.c_int32 * max(1, len(obs_index)))(*obs_index)
         spec.act_index = ctypes.cast(self._ai, ctypes.POINTER(ctypes.c_int32))

@@ -165,3 +165,51 @@ def test_non_finite_state_resets_only_that_env():
         assert np.allclose(eb.qpos[e, :15], model.fields["qpos0"], atol=1e-6) and not eb.qvel[e].any()
     assert np.isfinite(eb.qpos).all() and np.isfinite(eb.qvel).all()
     assert not np.array_equal(eb.qpos[0], healthy[0]) and abs(eb.qpos[0, 2] - healthy[0, 2]) < 0.1
+
+
+@pytest.mark.parametrize("scene,n", [("2A", 6), ("1A", 5)])
+def test_reset_noise_is_bounded_seeded_and_off_by_default(scene, n):
+    """`reset_noise` (config "resetNoise", new: the reference always restarts at qpos0): hinge / slide qpos within
+    +-noise of qpos0, free joints untouched, qvel within +-noise; different per env and per reset, identical for the
+    same seed; also with two envs per warp ("1A") and a masked reset."""
+    model, tables, agents, fj = load_scene(scene)
+    f = model.fields
+    qpos0 = f["qpos0"]
+    hinge = np.array([int(f["jnt_qposadr"][j]) for j in range(model.njnt) if int(f["jnt_type"][j]) != L.JNT_FREE])
+    other = np.setdiff1d(np.arange(model.nq), hinge)
+
+    def fresh(noise, seed=3):
+        spec, keep = make_spec(model, tables, agents, fj)
+        spec.reset_noise, spec.seed = noise, seed
+        eb = E.EmuBatch(model.blob, spec, n, keep)
+        eb.run(E.MODE_RESET)
+        return eb
+    plain = fresh(0.0)
+    assert np.allclose(plain.qpos[:, :model.nq], qpos0, atol=1e-6) and not plain.qvel.any()
+    a, b, c = fresh(0.1), fresh(0.1), fresh(0.1, seed=4)
+    d = a.qpos[:, :model.nq] - qpos0
+    assert np.abs(d[:, hinge]).max() <= 0.1 + 1e-6 and np.abs(d[:, hinge]).min() > 0
+    assert np.abs(d[:, other]).max() < 1e-6
+    assert np.abs(a.qvel[:, :model.nv]).max() <= 0.1 + 1e-6 and np.abs(a.qvel[:, :model.nv]).min() > 0
+    assert len({a.qpos[e].tobytes() for e in range(n)}) == n
+    assert np.array_equal(a.qpos, b.qpos) and np.array_equal(a.qvel, b.qvel)
+    assert not np.array_equal(a.qpos, c.qpos)
+    # the observation returned by reset is that of the perturbed state
+    od = a.spec.obs_dim[0]
+    assert rel_err(a.obs[0, 0, od - model.nv:od], a.qvel[0, :model.nv]) < 1e-6
+    # a later (masked) reset draws again and leaves the other envs alone
+    first = a.qpos.copy()
+    n_phys = a.spec.n_phys_act
+    a.actions[:, :, :n_phys] = 0.3
+    for _ in range(3):
+        a.run(E.MODE_STEP)
+    stepped = a.qpos.copy()
+    mask = np.zeros(n, np.uint8)
+    mask[1] = mask[n - 1] = 1
+    a.run(E.MODE_RESET, mask=mask)
+    for e in range(n):
+        if mask[e]:
+            assert np.abs(a.qpos[e, hinge] - qpos0[hinge]).max() <= 0.1 + 1e-6
+            assert not np.array_equal(a.qpos[e], first[e])
+        else:
+            assert np.array_equal(a.qpos[e], stepped[e])
