@@ -23,69 +23,106 @@ namespace mjb {
 
 struct RenderCams { int n; int id[RENDER_MAX_CAMS]; };
 
-// ray / box by slabs: the same first non-negative face crossing ray_geom enumerates face by face, in a third of
-// the instructions (boxes — arena walls, targets — are what most camera rays test)
-MJB_DEV float ray_box_slabs(f3 pos, const float* R, const float* size, f3 pnt, f3 vec) {
-  f3 lp = mulTv(R, pnt - pos), lv = mulTv(R, vec);
-  float tn = -MJB_BIG, tf = MJB_BIG;
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    const float p = comp(lp, a), v = comp(lv, a), s = size[a];
-    if (fabsf(v) < MJB_MINVAL) {
-      if (fabsf(p) > s) return -1.f;
-    } else {
-      const float inv = 1.f / v, t1 = (-s - p) * inv, t2 = (s - p) * inv;
-      tn = fmaxf(tn, fminf(t1, t2));
-      tf = fminf(tf, fmaxf(t1, t2));
-    }
+// ---- ray tests in the geom's local frame (lp = R^T (o - pos) is shared by all rays of a camera, lv = R^T d) ------
+// Same first non-negative crossing as ray_geom (step_kernel.cuh) / the oracle; boxes by slabs instead of face by
+// face (a third of the instructions; arena walls and target boxes are what most camera rays test).
+MJB_DEV float ray_local(int type, const float* size, f3 lp, f3 lv) {
+  if (type == MJB_GEOM_PLANE) {
+    if (lv.z > -MJB_MINVAL) return -1.f;
+    float x = -lp.z / lv.z;
+    if (x < 0) return -1.f;
+    float p0 = lp.x + x * lv.x, p1 = lp.y + x * lv.y;
+    return ((size[0] <= 0 || fabsf(p0) <= size[0]) && (size[1] <= 0 || fabsf(p1) <= size[1])) ? x : -1.f;
   }
-  if (tn > tf || tf < 0.f) return -1.f;
-  return tn >= 0.f ? tn : tf;
+  if (type == MJB_GEOM_SPHERE) {   // lv is a unit vector
+    float b = dot(lv, lp), det = b * b - (dot(lp, lp) - size[0] * size[0]);
+    if (det < 0) return -1.f;
+    float sq = sqrtf(det), x0 = -b - sq, x1 = -b + sq;
+    return x0 >= 0 ? x0 : (x1 >= 0 ? x1 : -1.f);
+  }
+  if (type == MJB_GEOM_BOX) {
+    float tn = -MJB_BIG, tf = MJB_BIG;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float p = comp(lp, a), v = comp(lv, a), s = size[a];
+      if (fabsf(v) < MJB_MINVAL) {
+        if (fabsf(p) > s) return -1.f;
+      } else {
+        const float inv = 1.f / v, t1 = (-s - p) * inv, t2 = (s - p) * inv;
+        tn = fmaxf(tn, fminf(t1, t2));
+        tf = fminf(tf, fmaxf(t1, t2));
+      }
+    }
+    if (tn > tf || tf < 0.f) return -1.f;
+    return tn >= 0.f ? tn : tf;
+  }
+  // capsule: cylinder side, then the two end spheres
+  float best = -1.f;
+  const float r = size[0], h = size[1];
+  float x[2];
+  if (quad_roots(lv.x * lv.x + lv.y * lv.y, lp.x * lv.x + lp.y * lv.y, lp.x * lp.x + lp.y * lp.y - r * r, x))
+    for (int i = 0; i < 2; i++)
+      if (fabsf(lp.z + x[i] * lv.z) <= h && x[i] >= 0 && (best < 0 || x[i] < best)) best = x[i];
+  for (int sg = -1; sg <= 1; sg += 2) {
+    f3 d = lp - mk3(0, 0, sg * h);
+    if (quad_roots(dot(lv, lv), dot(lv, d), dot(d, d) - r * r, x))
+      for (int i = 0; i < 2; i++)
+        if (sg * (lp.z + x[i] * lv.z) >= h && x[i] >= 0 && (best < 0 || x[i] < best)) best = x[i];
+  }
+  return best;
 }
 
-// colour of the first geom along the ray (o, unit d); packed 0x00BBGGRR
-MJB_DEV_NOINLINE uint32_t shade_ray(const float* GL, const uint16_t* list, int nlist, f3 o, f3 d) {
-  float best = MJB_BIG;
-  int bi = -1;
+// |normal . direction| at the hit, in the geom's local frame
+MJB_DEV float hit_cosine(int type, const float* size, f3 lp, f3 lv, float t) {
+  if (type == MJB_GEOM_PLANE) return fabsf(lv.z);
+  f3 p = lp + lv * t;
+  if (type == MJB_GEOM_SPHERE) return fabsf(dot(p, lv)) * MJB_RSQRT(fmaxf(dot(p, p), 1e-20f));
+  if (type == MJB_GEOM_CAPSULE) {
+    f3 n = mk3(p.x, p.y, p.z - fminf(fmaxf(p.z, -size[1]), size[1]));
+    return fabsf(dot(n, lv)) * MJB_RSQRT(fmaxf(dot(n, n), 1e-20f));
+  }
+  float ax = fabsf(p.x) / size[0], ay = fabsf(p.y) / size[1], az = fabsf(p.z) / size[2];   // box: the face reached
+  return (ax >= ay && ax >= az) ? fabsf(lv.x) : (ay >= az ? fabsf(lv.y) : fabsf(lv.z));
+}
+
+// colours of the first geom along 4 rays that share the origin `o` (unit directions d[4]); geom-outer loop: one
+// geom record load and one local origin serve all four rays.  Packed 0x00BBGGRR each.
+MJB_DEV_NOINLINE void shade_rays4(const float* GL, const uint16_t* list, int nlist, f3 o, const f3* d, uint32_t* col) {
+  float best[4] = {MJB_BIG, MJB_BIG, MJB_BIG, MJB_BIG};
+  int bi[4] = {-1, -1, -1, -1};
   MJB_NOUNROLL
   for (int i = 0; i < nlist; i++) {   // ascending geom ids: ties resolve as in the oracle's loop
     const int g = list[i];
     const float* G = GL + g * GL_STRIDE;
     const int type = __float_as_int(G[GL_TYPE]);
-    f3 pos = ld3(G + GL_POS);
-    if (type != MJB_GEOM_PLANE) {  // bounding sphere first
-      f3 oc = pos - o;
-      float tca = dot(oc, d), l2 = dot(oc, oc), rb = G[GL_RBOUND];
-      if (l2 - tca * tca > rb * rb || (tca < 0.f && l2 > rb * rb) || tca - rb > best) continue;
-    }
-    float t = type == MJB_GEOM_BOX ? ray_box_slabs(pos, G + GL_MAT, G + GL_SIZE, o, d) : ray_geom(pos, G + GL_MAT, G + GL_SIZE, o, d, type);
-    if (t >= 0.f && t < best) { best = t; bi = g; }
-  }
-  if (bi < 0) return 0u;
-  const float* G = GL + bi * GL_STRIDE;
-  const int type = __float_as_int(G[GL_TYPE]);
-  const float* R = G + GL_MAT;
-  float nd;  // |normal . direction|
-  if (type == MJB_GEOM_PLANE) {
-    nd = fabsf(dot(colv(R, 2), d));
-  } else if (type == MJB_GEOM_SPHERE) {
-    f3 n = (o + d * best) - ld3(G + GL_POS);
-    nd = fabsf(dot(n, d)) * MJB_RSQRT(fmaxf(dot(n, n), 1e-20f));
-  } else {
-    f3 lp = mulTv(R, (o + d * best) - ld3(G + GL_POS)), ld = mulTv(R, d);
-    if (type == MJB_GEOM_CAPSULE) {
-      float h = G[GL_SIZE + 1];
-      f3 n = mk3(lp.x, lp.y, lp.z - fminf(fmaxf(lp.z, -h), h));
-      nd = fabsf(dot(n, ld)) * MJB_RSQRT(fmaxf(dot(n, n), 1e-20f));
-    } else {  // box: the face whose scaled coordinate is largest
-      float ax = fabsf(lp.x) / G[GL_SIZE], ay = fabsf(lp.y) / G[GL_SIZE + 1], az = fabsf(lp.z) / G[GL_SIZE + 2];
-      nd = (ax >= ay && ax >= az) ? fabsf(ld.x) : (ay >= az ? fabsf(ld.y) : fabsf(ld.z));
+    const f3 oc = ld3(G + GL_POS) - o;
+    const float l2 = dot(oc, oc), rb = G[GL_RBOUND], rb2 = rb * rb;
+    const bool inside = l2 <= rb2 || type == MJB_GEOM_PLANE;   // no bounding-sphere rejection possible
+    float R[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = G[GL_MAT + k];
+    const f3 lp = type == MJB_GEOM_SPHERE ? oc * -1.f : mulTv(R, oc * -1.f);   // spheres stay in world axes
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (!inside) {
+        float tca = dot(oc, d[j]);
+        if (tca < 0.f || l2 - tca * tca > rb2 || tca - rb > best[j]) continue;
+      }
+      float t = ray_local(type, G + GL_SIZE, lp, type == MJB_GEOM_SPHERE ? d[j] : mulTv(R, d[j]));
+      if (t >= 0.f && t < best[j]) { best[j] = t; bi[j] = g; }
     }
   }
-  const float I = RENDER_AMBIENT + RENDER_DIFFUSE * fminf(nd, 1.f);
-  uint32_t r = (uint32_t)(G[GL_RGB] * I * 255.f + 0.5f), gg = (uint32_t)(G[GL_RGB + 1] * I * 255.f + 0.5f),
-           bb = (uint32_t)(G[GL_RGB + 2] * I * 255.f + 0.5f);
-  return r | (gg << 8) | (bb << 16);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (bi[j] < 0) { col[j] = 0u; continue; }
+    const float* G = GL + bi[j] * GL_STRIDE;
+    const int type = __float_as_int(G[GL_TYPE]);
+    const f3 lp = mulTv(G + GL_MAT, o - ld3(G + GL_POS)), lv = mulTv(G + GL_MAT, d[j]);
+    const float I = RENDER_AMBIENT + RENDER_DIFFUSE * fminf(hit_cosine(type, G + GL_SIZE, lp, lv, best[j]), 1.f);
+    uint32_t r = (uint32_t)(G[GL_RGB] * I * 255.f + 0.5f), gg = (uint32_t)(G[GL_RGB + 1] * I * 255.f + 0.5f),
+             bb = (uint32_t)(G[GL_RGB + 2] * I * 255.f + 0.5f);
+    col[j] = r | (gg << 8) | (bb << 16);
+  }
 }
 
 #if !defined(MJB_HOST_EMU)
@@ -201,9 +238,10 @@ __global__ void __launch_bounds__(256) k_render(const __grid_constant__ DevModel
         const uint16_t* L = TL + t * lstride;
         const int nl = L[0];
         uint32_t col[4];
+        f3 d[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          col[j] = (ix0 + j < width) ? shade_ray(GL, L + 1, nl, o, pixel_dir(cw, th, ix0 + j + 0.5f, iy + 0.5f, width, height)) : 0u;
+        for (int j = 0; j < 4; j++) d[j] = pixel_dir(cw, th, ix0 + j + 0.5f, iy + 0.5f, width, height);   // columns past the edge are not stored
+        shade_rays4(GL, L + 1, nl, o, d, col);
         uint8_t* dst = out + ((((size_t)env * cams.n + k) * height + iy) * width + ix0) * 3;
         if (words) {  // 12 bytes = three aligned words
           uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
