@@ -19,7 +19,6 @@ import argparse
 import json
 import multiprocessing as mp
 import os
-import subprocess
 import sys
 import threading
 import time

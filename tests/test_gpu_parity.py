@@ -608,3 +608,43 @@ def test_step_host_matches_device_step(monkeypatch, scene_xml, agents, n, pinned
         for name, got in (("obs", h_obs), ("reward", h_rew), ("term", h_term), ("trunc", h_trunc)):
             assert np.array_equal(got, getattr(dev.batch, name).cpu().numpy()), (t, name)
         assert torch.equal(hb.qpos, dev.batch.qpos)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("xml,free_joint", [("two_ants_touch_acc.xml", False), ("two_ants_touch_acc.xml", True), ("box_rangefinder.xml", True)])
+def test_parallel_api_conformance(xml, free_joint):
+    """The checks of the reference's own API test (tests/parallel_env_test.py -> pettingzoo parallel_api_test) and of
+    tests/sensor_test.py (observations stay inside the declared sensor bounds), restated without pettingzoo:
+    stable space objects, dict keys = agents (+ "__all__" where the reference adds it), observations of the declared
+    shape inside [low, high], numeric rewards, boolean flags, truncation from call maxSteps + 1 on (the reference's off-by-one)."""
+    import os
+    from common import LEVELS
+    from mujoco_rl_environment_wrapper_b200 import plugins as P
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    two = xml.startswith("two_ants")
+    agents = ["sender", "receiver"] if two else ["receiver"]
+    cfg = {"xmlPath": os.path.join(LEVELS, xml), "agents": agents, "freeJoint": free_joint, "skipFrames": 5, "maxSteps": 40}
+    if two:
+        cfg.update(environmentDynamics=[P.Language], infoJson=os.path.join(LEVELS, "info_2A.json"),
+                   rewardFunctions=[P.tag_distance_reward], doneFunctions=[P.distance_done])
+    env = MuJoCoRL(cfg)
+    assert env.agents == agents and env.possible_agents == agents
+    for a in agents:
+        assert env.observation_space(a) is env.observation_space(a) and env.action_space(a) is env.action_space(a)
+    obs, infos = env.reset()
+    assert set(obs) == set(agents) and set(infos) == set(agents)
+    finite_bounds = 0
+    for t in range(42):
+        act = {a: env.action_space(a).sample() for a in agents}
+        obs, rew, term, trunc, infos = env.step(act)
+        assert set(obs) == set(rew) == set(infos) == set(agents)
+        assert set(trunc) == set(agents) | {"__all__"}
+        assert set(term) == (set(agents) | {"__all__"} if two else set(agents))   # "__all__" only with done functions
+        for a in agents:
+            sp = env.observation_space(a)
+            assert obs[a].shape == sp.low.shape and np.isfinite(obs[a]).all()
+            assert (obs[a] >= sp.low - 1e-6).all() and (obs[a] <= sp.high + 1e-6).all(), (t, a)
+            finite_bounds = int(np.isfinite(sp.high).sum())
+            assert isinstance(rew[a], (int, float)) and isinstance(term[a], bool) and isinstance(trunc[a], bool)
+        assert trunc["__all__"] == (t >= 40)   # the check runs before the counter advances (mujoco_rl.py:279,288)
+    assert finite_bounds > 0, "the level must declare bounded sensors"
