@@ -186,27 +186,27 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
   for (int i = lane; i < dm.nq; i += 32) {
     int k, j;
     split_copy(i, dm.nq1, K, k, j);
-    qpos[i] = (fresh(k) || !has(k)) ? CF(qpos0)[i] : B.qpos[(size_t)(e0 + k) * dm.qpos_stride + j];
+    qpos[i] = (fresh(k) || !has(k)) ? CF(qpos0)[i] : MJB_LDG(&B.qpos[(size_t)(e0 + k) * dm.qpos_stride + j]);
   }
   MJB_NOUNROLL
   for (int i = lane; i < dm.nv; i += 32) {
     int k, j;
     split_copy(i, dm.nv1, K, k, j);
     bool z = fresh(k) || !has(k);
-    qvel[i] = z ? 0.f : B.qvel[(size_t)(e0 + k) * dm.qvel_stride + j];
-    qacc[i] = z ? 0.f : B.warmstart[(size_t)(e0 + k) * dm.qvel_stride + j];
+    qvel[i] = z ? 0.f : MJB_LDG(&B.qvel[(size_t)(e0 + k) * dm.qvel_stride + j]);
+    qacc[i] = z ? 0.f : MJB_LDG(&B.warmstart[(size_t)(e0 + k) * dm.qvel_stride + j]);
   }
   MJB_NOUNROLL
   for (int i = lane; i < dm.nu; i += 32) {
     int k, j;
     split_copy(i, dm.nu1, K, k, j);
-    ctrl[i] = (fresh(k) || !has(k)) ? 0.f : B.ctrl[(size_t)(e0 + k) * dm.ctrl_stride + j];
+    ctrl[i] = (fresh(k) || !has(k)) ? 0.f : MJB_LDG(&B.ctrl[(size_t)(e0 + k) * dm.ctrl_stride + j]);
   }
   MJB_NOUNROLL
   for (int i = lane; i < dm.nsensordata; i += 32) {
     int k, j;
     split_copy(i, dm.ns1, K, k, j);
-    sens[i] = (fresh(k) || !has(k)) ? 0.f : B.sensordata[(size_t)(e0 + k) * dm.sensor_stride + j];
+    sens[i] = (fresh(k) || !has(k)) ? 0.f : MJB_LDG(&B.sensordata[(size_t)(e0 + k) * dm.sensor_stride + j]);
   }
   if (mode == MODE_RESET && dm.reset_noise > 0.f) {
     // optional decorrelated starts (off by default: the reference always restarts at qpos0).  The draw is keyed by
@@ -244,7 +244,7 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
   for (int i = lane; i < 4 * dm.nprobe; i += 32) {
     int k, p1;
     probe_slot(i >> 2, k, p1);
-    probe[i] = has(k) ? B.probe[((size_t)(e0 + k) * dm.np1 + p1) * 4 + (i & 3)] : 0.f;
+    probe[i] = has(k) ? MJB_LDG(&B.probe[((size_t)(e0 + k) * dm.np1 + p1) * 4 + (i & 3)]) : 0.f;
   }
   // unpacked case: fetch the plugin store rows, dynamic actions and step counter of the env now, so that their
   // global-memory latency overlaps the state loads / the physics; consumed by the epilogue

@@ -859,10 +859,10 @@ MJB_DEV_NOINLINE float factor_solve_regT(const float* A, float* Lout, int lane, 
   for (int kk = NBT - 1; kk >= 0; kk--) {
     const int k = t0 + kk;
     float xk = MJB_SHFL(x * invd, k);
-    if (own && k < t1) {
-      if (lane == k) x = xk;
-      else if (lane < k) x -= Lout[colbase + kk * t0 + (kk * (kk + 1)) / 2] * xk;
-    }
+    // branch-free: lanes outside the block (or at / past column k) read a valid dummy word and keep x
+    const bool in = own && k < t1;
+    const float l = Lout[(in && lane < k) ? colbase + kk * t0 + (kk * (kk + 1)) / 2 : 0];
+    x = (in && lane == k) ? xk : ((in && lane < k) ? x - l * xk : x);
   }
   return x;
 }

@@ -23,6 +23,7 @@
 #define MJB_RSQRT(x) (1.0f / sqrtf(x))
 inline uint32_t mjb_f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 #define MJB_F2U(x) mjb_f2u(x)
+#define MJB_LDG(p) (*(p))
 #define MJB_CTA_SYNC(nthreads) ((void)0)
 #define MJB_CTA_ANY(nthreads, pred) (pred)
 #else
@@ -38,6 +39,9 @@ inline uint32_t mjb_f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 #define MJB_FFS(x) __ffs(x)
 #define MJB_RSQRT(x) rsqrtf(x)
 #define MJB_F2U(x) __float_as_uint(x)
+// read-only global load: lets the compiler batch the state-row loads ahead of the shared-memory stores between them
+// (every row is read once, at the start of its env, and written once, at the end, by the same warp)
+#define MJB_LDG(p) __ldg(p)
 // CTA-level alignment of the env-warps that are busy in this round (named barrier 1 with an explicit
 // thread count, so idle warps of a partial round do not take part).  nthreads == 0 disables it.
 __device__ __forceinline__ void mjb_cta_sync(int nthreads) {
