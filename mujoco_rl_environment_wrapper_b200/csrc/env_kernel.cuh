@@ -186,28 +186,65 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
   for (int i = lane; i < dm.nq; i += 32) {
     int k, j;
     split_copy(i, dm.nq1, K, k, j);
-    qpos[i] = (fresh(k) || !has(k)) ? CF(qpos0)[i] : MJB_LDG(&B.qpos[(size_t)(e0 + k) * dm.qpos_stride + j]);
+    if (fresh(k) || !has(k)) qpos[i] = CF(qpos0)[i];
+    else MJB_G2S(&qpos[i], &B.qpos[(size_t)(e0 + k) * dm.qpos_stride + j]);
   }
   MJB_NOUNROLL
   for (int i = lane; i < dm.nv; i += 32) {
     int k, j;
     split_copy(i, dm.nv1, K, k, j);
     bool z = fresh(k) || !has(k);
-    qvel[i] = z ? 0.f : MJB_LDG(&B.qvel[(size_t)(e0 + k) * dm.qvel_stride + j]);
-    qacc[i] = z ? 0.f : MJB_LDG(&B.warmstart[(size_t)(e0 + k) * dm.qvel_stride + j]);
+    if (z) { qvel[i] = 0.f; qacc[i] = 0.f; }
+    else {
+      MJB_G2S(&qvel[i], &B.qvel[(size_t)(e0 + k) * dm.qvel_stride + j]);
+      MJB_G2S(&qacc[i], &B.warmstart[(size_t)(e0 + k) * dm.qvel_stride + j]);
+    }
   }
   MJB_NOUNROLL
   for (int i = lane; i < dm.nu; i += 32) {
     int k, j;
     split_copy(i, dm.nu1, K, k, j);
-    ctrl[i] = (fresh(k) || !has(k)) ? 0.f : MJB_LDG(&B.ctrl[(size_t)(e0 + k) * dm.ctrl_stride + j]);
+    if (fresh(k) || !has(k)) ctrl[i] = 0.f;
+    else MJB_G2S(&ctrl[i], &B.ctrl[(size_t)(e0 + k) * dm.ctrl_stride + j]);
   }
   MJB_NOUNROLL
   for (int i = lane; i < dm.nsensordata; i += 32) {
     int k, j;
     split_copy(i, dm.ns1, K, k, j);
-    sens[i] = (fresh(k) || !has(k)) ? 0.f : MJB_LDG(&B.sensordata[(size_t)(e0 + k) * dm.sensor_stride + j]);
+    if (fresh(k) || !has(k)) sens[i] = 0.f;
+    else MJB_G2S(&sens[i], &B.sensordata[(size_t)(e0 + k) * dm.sensor_stride + j]);
   }
+  // exported positions: virtual probe order is [agents of every copy ..., targets of every copy ...]
+  auto probe_slot = [&](int p, int& k, int& p1) {
+    if (K == 1) { k = 0; p1 = p; }
+    else if (p < K * dm.a1) { k = p / dm.a1; p1 = p - k * dm.a1; }
+    else { int q = p - K * dm.a1; k = q / dm.t1; p1 = dm.a1 + (q - k * dm.t1); }
+  };
+  MJB_NOUNROLL
+  for (int i = lane; i < 4 * dm.nprobe; i += 32) {
+    int k, p1;
+    probe_slot(i >> 2, k, p1);
+    if (has(k)) MJB_G2S(&probe[i], &B.probe[((size_t)(e0 + k) * dm.np1 + p1) * 4 + (i & 3)]);
+    else probe[i] = 0.f;
+  }
+  // unpacked case: fetch the plugin store rows, dynamic actions and step counter of the env now, so that their
+  // global-memory latency overlaps the state loads / the physics; consumed by the epilogue
+  const bool epi = (mode == MODE_STEP || mode == MODE_RESET);
+  int pre_si[2] = {0, 0}, pre_ts = 0;
+  float pre_sf = 0.f, pre_act[2] = {0.f, 0.f};
+  if (epi && K == 1) {
+    const int* gsi = B.store_i + (size_t)e0 * dm.a1 * dm.store_i32;
+    const float* gsf = B.store_f + (size_t)e0 * dm.a1 * dm.store_f32;
+    const float* gact = B.actions + (size_t)e0 * dm.a1 * dm.act_stride;
+    for (int r = 0; r < 2; r++) {
+      int i = lane + 32 * r;
+      if (i < dm.a1 * dm.store_i32) pre_si[r] = gsi[i];
+      if (i < dm.a1 * dm.act_stride) pre_act[r] = gact[i];
+    }
+    if (lane < dm.a1 * dm.store_f32) pre_sf = gsf[lane];
+    if (lane == 0) pre_ts = B.timestep[e0];
+  }
+  MJB_G2S_WAIT();
   if (mode == MODE_RESET && dm.reset_noise > 0.f) {
     // optional decorrelated starts (off by default: the reference always restarts at qpos0).  The draw is keyed by
     // (seed, env, joint / dof) and by how the previous episode ended, so that it differs from reset to reset.
@@ -234,46 +271,29 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
       qvel[i] = dm.reset_noise * (2.f * u - 1.f);
     }
   }
-  // exported positions: virtual probe order is [agents of every copy ..., targets of every copy ...]
-  auto probe_slot = [&](int p, int& k, int& p1) {
-    if (K == 1) { k = 0; p1 = p; }
-    else if (p < K * dm.a1) { k = p / dm.a1; p1 = p - k * dm.a1; }
-    else { int q = p - K * dm.a1; k = q / dm.t1; p1 = dm.a1 + (q - k * dm.t1); }
-  };
-  MJB_NOUNROLL
-  for (int i = lane; i < 4 * dm.nprobe; i += 32) {
-    int k, p1;
-    probe_slot(i >> 2, k, p1);
-    probe[i] = has(k) ? MJB_LDG(&B.probe[((size_t)(e0 + k) * dm.np1 + p1) * 4 + (i & 3)]) : 0.f;
-  }
-  // unpacked case: fetch the plugin store rows, dynamic actions and step counter of the env now, so that their
-  // global-memory latency overlaps the state loads / the physics; consumed by the epilogue
-  const bool epi = (mode == MODE_STEP || mode == MODE_RESET);
-  int pre_si[2] = {0, 0}, pre_ts = 0;
-  float pre_sf = 0.f, pre_act[2] = {0.f, 0.f};
-  if (epi && K == 1) {
-    const int* gsi = B.store_i + (size_t)e0 * dm.a1 * dm.store_i32;
-    const float* gsf = B.store_f + (size_t)e0 * dm.a1 * dm.store_f32;
-    const float* gact = B.actions + (size_t)e0 * dm.a1 * dm.act_stride;
-    for (int r = 0; r < 2; r++) {
-      int i = lane + 32 * r;
-      if (i < dm.a1 * dm.store_i32) pre_si[r] = gsi[i];
-      if (i < dm.a1 * dm.act_stride) pre_act[r] = gact[i];
-    }
-    if (lane < dm.a1 * dm.store_f32) pre_sf = gsf[lane];
-    if (lane == 0) pre_ts = B.timestep[e0];
-  }
   MJB_SYNC();
   if (mode == MODE_STEP || mode == MODE_PHYSICS) {
     // apply_action (mujoco_parent.py:316-332): overwrite qvel (freeJoint) or ctrl
+    const int n_act = dm.n_agents * dm.n_phys_act;
+    const bool from_regs = K == 1 && epi && dm.a1 * dm.act_stride <= 64;   // the action rows were prefetched above
     MJB_NOUNROLL
-    for (int i = lane; i < dm.n_agents * dm.n_phys_act; i += 32) {
-      int av = i / dm.n_phys_act, k, a1;
+    for (int i0 = 0; i0 < n_act; i0 += 32) {
+      const int i = i0 + lane;
+      const bool on = i < n_act;
+      int av = on ? i / dm.n_phys_act : 0, k, a1;
       split_copy(av, dm.a1, K, k, a1);
-      if (!has(k)) continue;
-      float v = B.actions[((size_t)(e0 + k) * dm.a1 + a1) * dm.act_stride + (i - av * dm.n_phys_act)];
-      int idx = CI(act_index)[i];
-      if (dm.free_joint) qvel[idx] = v; else ctrl[idx] = v;
+      const int off = a1 * dm.act_stride + (on ? i - av * dm.n_phys_act : 0);
+      float v;
+      if (from_regs) {
+        const float lo = MJB_SHFL(pre_act[0], off & 31), hi = MJB_SHFL(pre_act[1], off & 31);
+        v = off < 32 ? lo : hi;
+      } else {
+        v = (on && has(k)) ? B.actions[(size_t)(e0 + k) * dm.a1 * dm.act_stride + off] : 0.f;
+      }
+      if (on && has(k)) {
+        int idx = CI(act_index)[i];
+        if (dm.free_joint) qvel[idx] = v; else ctrl[idx] = v;
+      }
     }
     MJB_SYNC();
   }

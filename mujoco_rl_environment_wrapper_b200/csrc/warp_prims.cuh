@@ -24,6 +24,8 @@
 inline uint32_t mjb_f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 #define MJB_F2U(x) mjb_f2u(x)
 #define MJB_LDG(p) (*(p))
+#define MJB_G2S(dst, src) (*(dst) = *(src))
+#define MJB_G2S_WAIT() ((void)0)
 #define MJB_CTA_SYNC(nthreads) ((void)0)
 #define MJB_CTA_ANY(nthreads, pred) (pred)
 #else
@@ -42,6 +44,13 @@ inline uint32_t mjb_f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 // read-only global load: lets the compiler batch the state-row loads ahead of the shared-memory stores between them
 // (every row is read once, at the start of its env, and written once, at the end, by the same warp)
 #define MJB_LDG(p) __ldg(p)
+// asynchronous 4-byte global -> shared copy (LDGSTS): the loads of a whole state row are in flight together and
+// the warp waits once (MJB_G2S_WAIT) instead of once per array
+__device__ __forceinline__ void mjb_g2s4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+#define MJB_G2S(dst, src) mjb_g2s4((dst), (src))
+#define MJB_G2S_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 // CTA-level alignment of the env-warps that are busy in this round (named barrier 1 with an explicit
 // thread count, so idle warps of a partial round do not take part).  nthreads == 0 disables it.
 __device__ __forceinline__ void mjb_cta_sync(int nthreads) {
