@@ -400,8 +400,10 @@ class MuJoCoRL:
         for lv in self._levels:
             lv["batch"].step()
         N = self.num_envs
+        A = len(self.agents)
+        flag = lambda t: t.view(torch.bool)   # the kernel writes 0 / 1 bytes: reinterpret, no extra kernel
         rewards = {agent: b.reward[:, a] for a, agent in enumerate(self.agents)}
-        terms = {agent: b.term[:, a].bool() for a, agent in enumerate(self.agents)}
+        terms = {agent: flag(b.term[:, a]) for a, agent in enumerate(self.agents)}
         infos = {agent: {dyn.__class__.__name__: {} for dyn in self._fused_dyn} for agent in self.agents}
         extra = {agent: [] for agent in self.agents}
         for dyn, lo, hi in self._host_dyn:  # user dynamics as batched torch code, agent-inner order
@@ -413,15 +415,18 @@ class MuJoCoRL:
                 infos[agent][dyn.__class__.__name__] = info
         for fn in self._host_rew:
             rewards = {agent: rewards[agent] + fn(self, agent) for agent in self.agents}
-        truncs = {agent: b.trunc[:, a].bool() for a, agent in enumerate(self.agents)}
-        truncs["__all__"] = b.trunc[:, len(self.agents)].bool()
+        truncs = {agent: flag(b.trunc[:, a]) for a, agent in enumerate(self.agents)}
+        truncs["__all__"] = flag(b.trunc[:, A])
         if self.done_functions:
-            for fn in self._host_done:
-                terms = {agent: terms[agent] | torch.as_tensor(fn(self, agent), device=self.device).bool() for agent in self.agents}
-            allt = terms[self.agents[0]].clone()
-            for agent in self.agents[1:]:
-                allt = allt | terms[agent]
-            terms["__all__"] = allt
+            if self._host_done or self._host_dyn:
+                for fn in self._host_done:
+                    terms = {agent: terms[agent] | torch.as_tensor(fn(self, agent), device=self.device).bool() for agent in self.agents}
+                allt = terms[self.agents[0]].clone()
+                for agent in self.agents[1:]:
+                    allt = allt | terms[agent]
+                terms["__all__"] = allt
+            else:
+                terms["__all__"] = flag(b.term[:, A])   # the kernel's own OR over the agents
         self.timestep += 1
         obs = self._collect_obs(extra)
         if N == 1:
