@@ -175,3 +175,32 @@ def test_get_camera_data_api():
         MuJoCoRL({"xmlPath": cfg["xmlPath"], "agents": cfg["agents"]}).get_camera_data("sender")
     nocam = MuJoCoRL({"xmlPath": os.path.join(LV, "two_ants.xml"), "agents": cfg["agents"], "agentCameras": True, "num_envs": 2})
     assert tuple(nocam.get_camera_data("sender").shape) == (2, 0, 64, 64, 3)
+
+
+@pytest.mark.gpu
+def test_cameras_follow_each_envs_level(tmp_path):
+    """xmlPath list + agentCameras: every env is rendered with the geometry / colours of its own level"""
+    import torch
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    a = open(os.path.join(LV, "two_ants_cams.xml")).read()
+    b = a.replace('size="0.5 0.5 0.5" rgba="0 0 255 1"', 'size="0.9 0.9 0.9" rgba="0 255 0 1"')
+    assert a != b
+    pa, pb = str(tmp_path / "A.xml"), str(tmp_path / "B.xml")
+    open(pa, "w").write(a)
+    open(pb, "w").write(b)
+    common = dict(agents=["sender", "receiver"], agentCameras=True, sensorResolution=(32, 32), num_envs=16, seed=5)
+    multi = MuJoCoRL(dict(common, xmlPath=[pa, pb]))
+    singles = [MuJoCoRL(dict(common, xmlPath=pa)), MuJoCoRL(dict(common, xmlPath=pb))]
+    for e in [multi] + singles:
+        e.reset()
+    lid = multi.level_id.cpu().numpy()
+    assert set(lid.tolist()) == {0, 1}
+    for t in range(3):
+        acts = multi.sample_actions()
+        for e in [multi] + singles:
+            e.step(acts)
+    got = multi.get_camera_data("sender").cpu().numpy()
+    want = [s.get_camera_data("sender").cpu().numpy() for s in singles]
+    for e in range(16):
+        assert np.array_equal(got[e], want[lid[e]][e]), e
+    assert not np.array_equal(want[0], want[1]), "the changed box must be visible to some camera"
