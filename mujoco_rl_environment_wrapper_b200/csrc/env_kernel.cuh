@@ -245,7 +245,7 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
     if (lane == 0) pre_ts = B.timestep[e0];
   }
   MJB_G2S_WAIT();
-  if (mode == MODE_RESET && dm.reset_noise > 0.f) {
+  if (MJB_UNLIKELY(mode == MODE_RESET && dm.reset_noise > 0.f)) {
     // optional decorrelated starts (off by default: the reference always restarts at qpos0).  The draw is keyed by
     // (seed, env, joint / dof) and by how the previous episode ended, so that it differs from reset to reset.
     MJB_SYNC();
@@ -312,7 +312,7 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
         bool bad = false;
         for (int j = lane; j < dm.nq1; j += 32) { float x = qpos[k * dm.nq1 + j]; bad |= !(fabsf(x) < 1e10f); }
         for (int j = lane; j < dm.nv1; j += 32) { float x = qvel[k * dm.nv1 + j]; bad |= !(fabsf(x) < 1e10f); }
-        if (MJB_BALLOT(bad)) {   // warp-uniform
+        if (MJB_UNLIKELY(MJB_BALLOT(bad))) {   // warp-uniform
           for (int j = lane; j < dm.nq1; j += 32) qpos[k * dm.nq1 + j] = CF(qpos0)[k * dm.nq1 + j];
           for (int j = lane; j < dm.nv1; j += 32) { qvel[k * dm.nv1 + j] = 0.f; qacc[k * dm.nv1 + j] = 0.f; }
           if (B.nreset && lane == 0 && ((upd >> k) & 1u)) B.nreset[e0 + k] += 1;

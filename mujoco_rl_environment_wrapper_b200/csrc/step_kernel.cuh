@@ -873,7 +873,7 @@ MJB_DEV float factor_solve_reg(const float* A, float* Lout, int lane, int t0, in
 }
 // (A + diag) x = b per block; picks the register path when the blocks are small enough
 MJB_DEV float factor_solve(const float* A, float* L, int lane, int t0, int t1, int nb, float diag_add, float b, int nv) {
-  if (nb <= MJB_NB) return factor_solve_reg(A, L, lane, t0, t1, nb, diag_add, b);
+  if (MJB_LIKELY(nb <= MJB_NB)) return factor_solve_reg(A, L, lane, t0, t1, nb, diag_add, b);
   if (A != L) {
     MJB_NOUNROLL
     for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) L[i] = A[i];

@@ -75,6 +75,10 @@ __device__ __forceinline__ bool mjb_cta_any(int nthreads, bool pred) {
 #define MJB_CTA_ANY(nthreads, pred) mjb_cta_any((nthreads), (pred))
 #endif
 
+// block-placement hints: rarely taken paths move out of the straight-line instruction stream
+#define MJB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define MJB_LIKELY(x) __builtin_expect(!!(x), 1)
+
 namespace mjb {
 
 MJB_DEV float wsum(float v) {
