@@ -65,6 +65,8 @@ namespace mjb {
   X(geom_ray)       /* int [ngeom]     1 if visible to rays (alpha != 0)                         */ \
   X(pair_pack)      /* u32 [npair]     g1 | g2 << 12 | class << 24  (sorted by type pair)        */ \
   X(pclass)         /* f32 [nclass*12] margin, includemargin, mu, K, B, solimp[5], condim, pad   */ \
+  X(bp_block)       /* [nblock*4]      pair blocks (tree x tree | tree x static geom): see BP_*  */ \
+  X(bp_passmask)    /* u32 [npass*2]   blocks present in each 32-pair pass of the broad phase    */ \
   X(site_mb)        /* int [nsite]                                                               */ \
   X(site_type)      /* int [nsite]                                                               */ \
   X(site_pos)       /* f32 [nsite*3]   local (or world when static)                              */ \
@@ -126,7 +128,7 @@ struct DevPlugin {
 struct DevModel {
   // sizes
   int nq, nv, nu, nmb, njnt, nlim, ngeom, ngdyn, nsite, nsensor, nsensordata, npair, nclass, nlevel, nprobe;
-  int maxcon, maxcand, maxefc, ldj, maxtree;
+  int maxcon, maxcand, maxefc, ldj, maxtree, nblock;
   // packing: `pack` real envs per warp (see replicate.h); the *1 sizes are those of ONE real env
   int pack, a1, t1, nq1, nv1, nu1, ns1, np1, ngeom1, maxcon1;
   int integrator, has_damping, need_acc_sensors;
@@ -170,5 +172,8 @@ enum { LIM_LO = 0, LIM_HI, LIM_MARGIN, LIM_K, LIM_B, LIM_INVW, LIM_SOLIMP, LIM_S
 enum { PC_MARGIN = 0, PC_INCMARGIN, PC_MU, PC_K, PC_B, PC_SOLIMP, PC_CONDIM = 10, PC_STRIDE = 12 };
 enum { DOF_AXIS = 0, DOF_FREE_TRANS = 1, DOF_FREE_ROT = 2 };
 enum { PROBE_BODY = 0, PROBE_GEOM = 1, PROBE_CONST = 2 };
+// pair block: root kernel body of tree A, root kernel body of tree B (or -1 - static geom id, or BP_ALWAYS),
+// reach of A + reach of B (trees) / reach of A (static partner), largest pair margin in the block
+enum { BP_ROOT_A = 0, BP_PARTNER = 1, BP_REACH = 2, BP_MARGIN = 3, BP_STRIDE = 4, BP_ALWAYS = 0x7fffffff };
 
 }  // namespace mjb

@@ -1,6 +1,7 @@
 // dev_model_build.h — host builder of the fp32 device image (see dev_model.h).
 #pragma once
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -245,11 +246,76 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   {
     std::vector<int> order(m.npair);
     for (int k = 0; k < m.npair; k++) order[k] = k;
+    // Pair blocks for the two-level broad phase: all pairs between one kinematic tree and another tree / one
+    // static geom.  A tree is bounded by a sphere about its root body's origin whose radius is the farthest any of
+    // its geoms can get from that origin in any joint configuration (`reach`, below); a 32-pair pass of the flat
+    // broad phase is skipped when none of its blocks can touch.
+    std::vector<double> reach_body(nbody, 0.0), reach_tree(nbody, 0.0);   // indexed by body / by root body
+    std::vector<int> root_of(nbody, 0);
+    for (int b = 1; b < nbody; b++) {
+      if (!moving[b]) continue;
+      int p = m.body_parentid[b];
+      if (!moving[p]) { root_of[b] = b; reach_body[b] = 0; continue; }
+      root_of[b] = root_of[p];
+      double jp = 0, slide = 0;
+      for (int j = m.body_jntadr[b]; j >= 0 && j < m.body_jntadr[b] + m.body_jntnum[b]; j++) {
+        jp = std::max(jp, std::sqrt(m.jnt_pos[3 * j] * m.jnt_pos[3 * j] + m.jnt_pos[3 * j + 1] * m.jnt_pos[3 * j + 1] + m.jnt_pos[3 * j + 2] * m.jnt_pos[3 * j + 2]));
+        if (m.jnt_type[j] == MJB_JNT_SLIDE)
+          slide += m.jnt_limited[j] ? std::max(std::fabs(m.jnt_range[2 * j]), std::fabs(m.jnt_range[2 * j + 1])) : 1e9;
+        if (m.jnt_type[j] == MJB_JNT_FREE) slide += 1e9;   // a free joint below the root: unbounded
+      }
+      double bp = std::sqrt(m.body_pos[3 * b] * m.body_pos[3 * b] + m.body_pos[3 * b + 1] * m.body_pos[3 * b + 1] + m.body_pos[3 * b + 2] * m.body_pos[3 * b + 2]);
+      reach_body[b] = reach_body[p] + bp + 2 * jp + slide;
+    }
+    for (int g = 0; g < m.ngeom; g++) {
+      int b = m.geom_bodyid[g];
+      if (!moving[b]) continue;
+      double gp = std::sqrt(m.geom_pos[3 * g] * m.geom_pos[3 * g] + m.geom_pos[3 * g + 1] * m.geom_pos[3 * g + 1] + m.geom_pos[3 * g + 2] * m.geom_pos[3 * g + 2]);
+      double r = m.geom_type[g] == MJB_GEOM_PLANE ? 1e9 : m.geom_rbound[g];
+      reach_tree[root_of[b]] = std::max(reach_tree[root_of[b]], reach_body[b] + gp + r);
+    }
+    auto group = [&](int g) { int b = m.geom_bodyid[g]; return moving[b] ? root_of[b] : -1 - g; };   // tree root body | static geom
+    std::map<std::pair<int, int>, int> block_id;
+    std::vector<std::array<double, 4>> blocks;   // rootA kernel body, partner, reach, margin
+    std::vector<int> pair_block(m.npair, 0);
+    for (int k = 0; k < m.npair; k++) {
+      int ga = group(m.pair_geom1[k]), gb = group(m.pair_geom2[k]);
+      if (ga < 0 && gb >= 0) std::swap(ga, gb);          // the tree first
+      else if (ga >= 0 && gb >= 0 && gb < ga) std::swap(ga, gb);
+      auto key = std::make_pair(ga, gb);
+      auto it = block_id.find(key);
+      int id;
+      if (it == block_id.end()) {
+        id = (int)blocks.size();
+        block_id[key] = id;
+        std::array<double, 4> rec{0, (double)BP_ALWAYS, 0, 0};
+        if (ga >= 0 && gb >= 0 && ga != gb) { rec = {(double)b2k[ga], (double)b2k[gb], reach_tree[ga] + reach_tree[gb], 0}; }
+        else if (ga >= 0 && gb < 0) { rec = {(double)b2k[ga], (double)gb, reach_tree[ga], 0}; }
+        blocks.push_back(rec);
+      } else id = it->second;
+      blocks[id][3] = std::max(blocks[id][3], m.pair_margin[k]);
+      pair_block[k] = id;
+    }
+    const bool use_blocks = !blocks.empty() && blocks.size() <= 64;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
       int ta = m.geom_type[m.pair_geom1[a]] * 16 + m.geom_type[m.pair_geom2[a]];
       int tb = m.geom_type[m.pair_geom1[b]] * 16 + m.geom_type[m.pair_geom2[b]];
+      if (use_blocks && pair_block[a] != pair_block[b]) return pair_block[a] < pair_block[b];
       return ta < tb;
     });
+    dm.nblock = use_blocks ? (int)blocks.size() : 0;
+    w.begin(IF_bp_block);
+    for (int i = 0; i < dm.nblock; i++) {
+      w.i((int)blocks[i][0]); w.i((int)blocks[i][1]); w.f(std::min(blocks[i][2], 1e9)); w.f(blocks[i][3]);
+    }
+    if (!dm.nblock) for (int i = 0; i < BP_STRIDE; i++) w.i(0);
+    w.begin(IF_bp_passmask);
+    for (int base = 0; base < std::max(1, m.npair); base += 32) {
+      uint64_t mask = 0;
+      for (int i = base; i < std::min(m.npair, base + 32); i++) mask |= use_blocks ? (1ull << pair_block[order[i]]) : ~0ull;
+      if (!use_blocks) mask = ~0ull;
+      w.u((uint32_t)(mask & 0xffffffffu)); w.u((uint32_t)(mask >> 32));
+    }
     std::map<std::vector<float>, int> classes;
     std::vector<std::vector<float>> class_list;
     std::vector<uint32_t> packed;

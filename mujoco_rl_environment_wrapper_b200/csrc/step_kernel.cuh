@@ -482,9 +482,43 @@ MJB_DEV int collide(const Ctx& c) {
   const uint32_t* pairs = CU(pair_pack);
   int* cand = SI(cand);
   int ncand = 0;
-  // broad phase: bounding spheres (planes: signed distance of the centre)
+  // broad phase, level 1: which pair blocks (tree x tree, tree x static geom) can touch at all — a tree is bounded
+  // by a sphere of radius `reach` about its root body's origin (dev_model_build.h)
+  uint32_t act_lo = 0xffffffffu, act_hi = 0xffffffffu;
+  MJB_NOUNROLL
+  for (int b0 = 0; b0 < dm.nblock; b0 += 32) {
+    const int bi = b0 + c.lane;
+    bool on = false;
+    if (bi < dm.nblock) {
+      const int* rec = CI(bp_block) + BP_STRIDE * bi;
+      const int partner = rec[BP_PARTNER];
+      if (partner == BP_ALWAYS) on = true;
+      else {
+        const float reach = CF(bp_block)[BP_STRIDE * bi + BP_REACH] + CF(bp_block)[BP_STRIDE * bi + BP_MARGIN];
+        const f3 ca = ld3(SF(xpos) + 3 * rec[BP_ROOT_A]);
+        if (partner >= 0) {
+          f3 d = ld3(SF(xpos) + 3 * partner) - ca;
+          on = dot(d, d) <= reach * reach;
+        } else {
+          const int g = -1 - partner;   // static geom: world pose is in the image
+          const f3 gp = ld3(CF(geom_pos) + 3 * g);
+          const float* gm = CF(geom_mat) + 9 * g;
+          const int type = CI(geom_type)[g];
+          if (type == MJB_GEOM_PLANE) on = dot(ca - gp, colv(gm, 2)) <= reach;
+          else if (type == MJB_GEOM_BOX) on = point_box_dist(mulTv(gm, ca - gp), CF(geom_size) + 3 * g) <= reach;
+          else { f3 d = gp - ca; float rr = reach + CF(geom_rbound)[g]; on = dot(d, d) <= rr * rr; }
+        }
+      }
+    }
+    const uint32_t bal = MJB_BALLOT(on);
+    if (b0 == 0) act_lo = bal; else act_hi = bal;
+  }
+  if (dm.nblock > 0 && dm.nblock <= 32) act_hi = 0;
+  // level 2: bounding spheres of the geoms (planes: signed distance of the centre), 32 pairs per pass
   MJB_NOUNROLL
   for (int base = 0; base < dm.npair; base += 32) {
+    const uint32_t* pm = CU(bp_passmask) + 2 * (base >> 5);
+    if (!((pm[0] & act_lo) | (pm[1] & act_hi))) continue;   // warp-uniform
     int p = base + c.lane;
     bool keep = false;
     if (p < dm.npair) {

@@ -213,3 +213,58 @@ def test_reset_noise_is_bounded_seeded_and_off_by_default(scene, n):
             assert not np.array_equal(a.qpos[e], first[e])
         else:
             assert np.array_equal(a.qpos[e], stepped[e])
+
+
+def test_two_level_broad_phase_never_drops_a_contact():
+    """The block-level cull (tree bounding sphere vs tree / static geom) is conservative: for ants teleported next to
+    walls, target boxes and each other with random joint angles, the contact set equals the oracle's, which tests
+    every pair."""
+    model, tables, agents, fj = load_scene("2A")
+    spec, keep = make_spec(model, tables, agents, fj)
+    f = model.fields
+    rng = np.random.default_rng(42)
+    N = 48
+    eb = E.EmuBatch(model.blob, spec, N, keep)
+    eb.run(E.MODE_RESET)
+    hinge = [int(f["jnt_qposadr"][j]) for j in range(model.njnt) if int(f["jnt_type"][j]) != L.JNT_FREE]
+    free = [int(f["jnt_qposadr"][j]) for j in range(model.njnt) if int(f["jnt_type"][j]) == L.JNT_FREE]
+    # places of interest: arena walls at about +-10 m, the three target boxes, mid-field
+    spots = [(9.3, 0.0), (-9.4, 1.0), (0.5, 4.3), (0.2, -4.4), (7.0, -2.0), (1.4, -2.1), (-5.5, -2.4), (0.0, 0.0), (3.0, 3.0)]
+    qpos = np.tile(f["qpos0"], (N, 1))
+    for e in range(N):
+        sx, sy = spots[rng.integers(len(spots))]
+        for k, qa in enumerate(free):
+            if k == 0 or rng.random() < 0.5:
+                qpos[e, qa:qa + 2] = [sx + rng.uniform(-1.2, 1.2), sy + rng.uniform(-1.2, 1.2)]
+            else:   # the second ant right next to the first
+                qpos[e, qa:qa + 2] = qpos[e, free[0]:free[0] + 2] + rng.uniform(-0.9, 0.9, 2)
+            qpos[e, qa + 2] = rng.uniform(0.3, 0.9)
+            q = rng.normal(size=4)
+            qpos[e, qa + 3:qa + 7] = q / np.linalg.norm(q)
+        qpos[e, hinge] += rng.uniform(-0.6, 0.6, len(hinge))
+    eb.qpos[:, :model.nq] = qpos
+    eb.qvel[:] = 0
+    eb.run(E.MODE_FORWARD)
+    sim = OracleSimLazy(model)
+    total = 0
+    kinds = set()
+    for e in range(N):
+        sim.array("qpos")[:] = qpos[e]
+        sim.array("qvel")[:] = 0
+        sim.forward()
+        want = sorted(sim.contact_pairs())
+        nc = eb.ncon[e]
+        got = sorted((int(a), int(b)) for a, b in eb.contact_geom[e, :nc])
+        if len(want) <= eb.layout.maxcon:
+            assert got == want, (e, got, want)
+        else:
+            assert set(got) <= set(want) and len(got) == eb.layout.maxcon
+        total += len(want)
+        for a, b in want:
+            kinds.add((int(f["geom_type"][a]), int(f["geom_type"][b])))
+    assert total > 60 and len(kinds) >= 4, (total, kinds)   # floor, walls / boxes, ant-ant contacts all occur
+
+
+def OracleSimLazy(model):
+    from oracle.sim import OracleSim
+    return OracleSim(model.blob)
