@@ -117,3 +117,34 @@ def test_primal_newton_equals_dual_pgs_at_convergence():
         worst = max(worst, np.abs(a.qvel - b.qvel).max())
     assert a.ncon > 0 or worst >= 0
     assert worst < 1e-8
+
+
+def test_oracle_against_mujoco_goldens():
+    """Pins the oracle to real MuJoCo trajectories when tests/golden/make_physics_golden.py could be run somewhere
+    (it needs `import mujoco`).  No golden file -> skipped, and physics parity stays UNPINNED."""
+    import glob
+    import os
+    import pytest
+    from mujoco_rl_environment_wrapper_b200 import _lib as L
+    from oracle.sim import OracleSim
+    here = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(glob.glob(os.path.join(here, "golden", "physics_*.npz")))
+    if not files:
+        pytest.skip("no MuJoCo physics goldens (mujoco is not installable in this environment)")
+    for path in files:
+        g = np.load(path)
+        scene = os.path.basename(path)[len("physics_"):-4] + ".xml"
+        model = L.Model(open(os.path.join(here, "levels", scene)).read())
+        sim = OracleSim(model.blob)
+        sim.reset()
+        # one-step parity from MuJoCo's own previous state (no drift accumulation), every 10th step
+        for t in range(1, len(g["qpos"]), 10):
+            sim.array("qpos")[:] = g["qpos"][t - 1]
+            sim.array("qvel")[:] = g["qvel"][t - 1]
+            if model.nu:
+                sim.array("ctrl")[:] = g["ctrl"][t]
+            sim.step()
+            assert np.allclose(sim.array("qpos"), g["qpos"][t], rtol=0, atol=1e-6), (scene, t)
+            assert np.allclose(sim.array("qvel"), g["qvel"][t], rtol=0, atol=1e-5), (scene, t)
+            want = sorted((int(a), int(b)) for tt, a, b in g["contact_pairs"] if tt == t)
+            assert sorted(sim.contact_pairs()) == want, (scene, t)
