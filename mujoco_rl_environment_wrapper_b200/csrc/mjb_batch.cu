@@ -165,13 +165,11 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStr
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, stream));
   }
-  // the first grid*warps envs are taken statically; the counter hands out the rest
-  int first = b->grid * b->warps;
+  // dynamic scheduler only: the first grid*warps envs are taken statically, the counter hands out the rest
   int* counter = b->d_next + b->next_slot;
   b->next_slot = (b->next_slot + 1) % 64;
   if (b->lockstep == 0)  // only the dynamic scheduler consumes the counter
     CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, stream));
-  (void)first;
   if (mode == mjb::MODE_STEP && b->has_lite) {
     // no physics in the step: many small envs per SM, rounds aligned the same way
     mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, stream>>>(b->lite.dm, b->d_image, b->B, b->num_envs, mode,

@@ -23,7 +23,6 @@
 #define MJB_RSQRT(x) (1.0f / sqrtf(x))
 inline uint32_t mjb_f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 #define MJB_F2U(x) mjb_f2u(x)
-#define MJB_LDG(p) (*(p))
 #define MJB_G2S(dst, src) (*(dst) = *(src))
 #define MJB_G2S_WAIT() ((void)0)
 #define MJB_CTA_SYNC(nthreads) ((void)0)
@@ -41,9 +40,6 @@ inline uint32_t mjb_f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 #define MJB_FFS(x) __ffs(x)
 #define MJB_RSQRT(x) rsqrtf(x)
 #define MJB_F2U(x) __float_as_uint(x)
-// read-only global load: lets the compiler batch the state-row loads ahead of the shared-memory stores between them
-// (every row is read once, at the start of its env, and written once, at the end, by the same warp)
-#define MJB_LDG(p) __ldg(p)
 // asynchronous 4-byte global -> shared copy (LDGSTS): the loads of a whole state row are in flight together and
 // the warp waits once (MJB_G2S_WAIT) instead of once per array
 __device__ __forceinline__ void mjb_g2s4(float* dst, const float* src) {
