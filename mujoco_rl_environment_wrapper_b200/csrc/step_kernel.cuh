@@ -850,53 +850,66 @@ MJB_DEV float chol_solve(const float* A, int lane, int t0, int t1, int nb, float
 // Register-resident variant for blocks of at most NBT rows (every level of the reference: 14 dofs per ant,
 // 6 for a free body): lane i keeps row i of its block in registers, row j is broadcast with shuffles, no
 // shared-memory traffic and no barriers inside the factorisation.  Solves (A + diag) x = b for the lane's
-// block where A is a packed lower triangle in shared memory; L is written to `Lout` (packed) for the
-// transposed solve.  Lanes of a block smaller than NBT (and idle lanes) run the same instruction stream on
-// garbage that is never stored: columns past the block's size only ever touch the unused upper triangle.
+// block where A is a packed lower triangle in shared memory.  Lanes of a block smaller than NBT (and idle
+// lanes) run the same instruction stream on garbage that is never stored: columns past the block's size only
+// ever touch the unused upper triangle.
+//
+// The factorisation is L D L' (unit lower L, no square roots), arranged for LATENCY, which is what this kernel
+// runs out of: lane i keeps t_ik = L_ik d_k (raw) and l_ik = L_ik.  Column j needs s_ij = a_ij - sum_k l_ik t_jk;
+// the raw t_jk of row j and the pivot d_j travel in two independent shuffles, so the dependent chain per column
+// is shuffle -> rcp -> mul -> fma (~55 cycles) instead of shuffle -> rsqrt -> mul -> shuffle -> fma (~90) of the
+// L L' form, and neither triangular solve divides.  The unit-lower L is written to `Lout` (packed) for the
+// transposed solve.
 #define MJB_NB 16
 template <int NBT>
 MJB_DEV_NOINLINE float factor_solve_regT(const float* A, float* Lout, int lane, int t0, int t1, float diag_add, float b) {
-  float a[NBT];
+  float t[NBT], l[NBT];
   const bool own = lane < t1;
   const int li = lane - t0;
   const int rowoff = own ? tri(lane, t0) : 0;
 #pragma unroll
   for (int k = 0; k < NBT; k++) {
     float v = (own && k <= li) ? A[rowoff + k] : 0.f;
-    a[k] = (k == li) ? v + diag_add : v;
+    t[k] = (k == li) ? v + diag_add : v;
   }
-  float invd = 1.f;
+  float rdi = 1.f;   // 1 / d_i of the lane's own row
 #pragma unroll
   for (int j = 0; j < NBT; j++) {
     const int src = t0 + j;
-    float s = a[j];
+    float s0 = t[j], s1 = 0.f;   // two partial sums: halves the fma chain of the late columns
 #pragma unroll
-    for (int k = 0; k < j; k++) s -= a[k] * MJB_SHFL(a[k], src);
-    float sj = MJB_SHFL(s, src);
-    float inv = MJB_RSQRT(fmaxf(sj, 1e-20f));
-    a[j] = (li == j ? sj : s) * inv;
-    if (li == j) invd = inv;
+    for (int k = 0; k < j; k++) {
+      const float tjk = MJB_SHFL(t[k], src);
+      if (k & 1) s1 -= l[k] * tjk; else s0 -= l[k] * tjk;
+    }
+    const float s = s0 + s1;
+    t[j] = s;                                             // d_j on lane src, raw t_ij below it
+    const float rd = 1.f / fmaxf(MJB_SHFL(s, src), 1e-20f);
+    l[j] = s * rd;                                        // L_ij (1 on the diagonal)
+    if (li == j) rdi = rd;
   }
 #pragma unroll
   for (int k = 0; k < NBT; k++)
-    if (own && k <= li) Lout[rowoff + k] = a[k];
+    if (own && k < li) Lout[rowoff + k] = l[k];
+  // L y = b
   float x = b;
 #pragma unroll
   for (int k = 0; k < NBT; k++) {
-    float yk = MJB_SHFL(x * invd, t0 + k);
-    x = (li == k) ? yk : (li > k ? x - a[k] * yk : x);
+    const float yk = MJB_SHFL(x, t0 + k);
+    x = li > k ? x - l[k] * yk : x;
   }
+  x *= rdi;   // D z = y
   MJB_SYNC();
-  // transposed solve: column k of L is contiguous across lanes in the packed store
+  // L' x = z: column k of L' is row k of L, contiguous across lanes in the packed store
   const int colbase = tri(t0, 0) + lane;  // &L(t0 + kk, lane) = colbase + kk * t0 + kk (kk + 1) / 2
 #pragma unroll
-  for (int kk = NBT - 1; kk >= 0; kk--) {
+  for (int kk = NBT - 1; kk >= 1; kk--) {
     const int k = t0 + kk;
-    float xk = MJB_SHFL(x * invd, k);
+    const float xk = MJB_SHFL(x, k);
     // branch-free: lanes outside the block (or at / past column k) read a valid dummy word and keep x
-    const bool in = own && k < t1;
-    const float l = Lout[(in && lane < k) ? colbase + kk * t0 + (kk * (kk + 1)) / 2 : 0];
-    x = (in && lane == k) ? xk : ((in && lane < k) ? x - l * xk : x);
+    const bool in = own && k < t1 && lane < k;
+    const float lk = Lout[in ? colbase + kk * t0 + (kk * (kk + 1)) / 2 : 0];
+    x = in ? x - lk * xk : x;
   }
   return x;
 }
