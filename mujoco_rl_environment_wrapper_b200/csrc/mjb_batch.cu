@@ -124,6 +124,7 @@ struct mjb_batch {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // host-buffer step: second half of the envs (copy / compute overlap)
   cudaEvent_t ev_fork = nullptr, ev_k0 = nullptr, ev_join = nullptr;
+  int host_zero_copy = 1;                    // MJB_HOST_ZEROCOPY: 1 = the kernel writes page-locked result arrays itself
   int host_split = 1;                        // MJB_HOST_SPLIT: 1 = pipeline the host-buffer step in two halves
   uint32_t* d_image = nullptr;
   int* d_next = nullptr;   // ring of work counters, one per in-flight launch
@@ -155,10 +156,12 @@ namespace {
   } while (0)
 
 // `base` / `count` (in envs, multiples of the pack factor) restrict the launch to a contiguous env range
-int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStream_t stream = nullptr, int base = 0, int count = -1) {
+int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStream_t stream = nullptr, int base = 0, int count = -1,
+           const mjb_buffers* out_buffers = nullptr) {
   if (b->subset && b->subset_count == 0) return MJB_OK;   // no env on this level right now
   if (!stream) stream = b->stream;
   const int active = b->subset ? b->subset_count : (count >= 0 ? count : b->num_envs);
+  const mjb_buffers& B = out_buffers ? *out_buffers : b->B;   // the host-buffer step redirects the result arrays
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (b->timing) {
     CUDA_TRY(cudaEventCreate(&e0));
@@ -172,7 +175,7 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStr
     CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, stream));
   if (mode == mjb::MODE_STEP && b->has_lite) {
     // no physics in the step: many small envs per SM, rounds aligned the same way
-    mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, stream>>>(b->lite.dm, b->d_image, b->B, b->num_envs, mode,
+    mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, stream>>>(b->lite.dm, b->d_image, B, b->num_envs, mode,
                                                                                    skip_frames, mask, counter, 2, b->subset, active, base);
   } else {
     auto kern = b->img.dm.pack > 1 ? mjb::k_env<true, true> : mjb::k_env<true, false>;
@@ -180,7 +183,7 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStr
     const bool ranged = count >= 0 && !b->subset;   // a range launch walks env ids directly
     const int need = ((active + pack - 1) / pack + b->warps - 1) / b->warps;
     kern<<<std::min(b->grid, std::max(1, need)), b->warps * 32, b->smem_bytes, stream>>>(
-        b->img.dm, b->d_image, b->B, b->num_envs, mode, skip_frames, mask, counter, b->lockstep | (b->groups << 8),
+        b->img.dm, b->d_image, B, b->num_envs, mode, skip_frames, mask, counter, b->lockstep | (b->groups << 8),
         b->subset ? b->subset : ((b->lockstep && pack == 1 && !ranged) ? b->env_order : nullptr), active, base / pack);
   }
   CUDA_TRY(cudaGetLastError());
@@ -301,6 +304,7 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
   }
   b->h_first[0] = b->grid * b->warps;
   b->host_split = mjb::env_int("MJB_HOST_SPLIT", 1);
+  b->host_zero_copy = mjb::env_int("MJB_HOST_ZEROCOPY", 1);
   if (cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&b->ev_k0, cudaEventDisableTiming) != cudaSuccess ||
@@ -390,11 +394,45 @@ int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward,
                           (const char*)b->B.term == d0 + r16(nb_obs) + r16(nb_rew) && (const char*)term == h0 + r16(nb_obs) + r16(nb_rew) &&
                           (const char*)b->B.trunc == d0 + r16(nb_obs) + r16(nb_rew) + r16(nb_flag) &&
                           (const char*)trunc == h0 + r16(nb_obs) + r16(nb_rew) + r16(nb_flag);
-  // Two halves on two streams: the second half's actions go up while the first half computes, and the first
-  // half's observations come down while the second half computes.  Same results (envs are independent).
+  // Page-locked result arrays are written by the kernel itself (zero-copy: pinned host memory is device-addressable,
+  // the stores are posted PCIe writes that overlap the rest of the step), so no device-to-host copy follows the
+  // kernel.  The actions still go up by copy engine, in two halves on two streams so that the second half's upload
+  // overlaps the first half's compute.  Same results (envs are independent).
   const int pack = dm.pack;
   int half = (int)((N / 2 + pack - 1) / pack * pack);
-  if (b->host_split && packed_out && !b->subset && b->lockstep != 0 && N >= (size_t)(4 * b->warps) && half > 0 && (size_t)half < N) {
+  const bool split = b->host_split && !b->subset && b->lockstep != 0 && N >= (size_t)(4 * b->warps) && half > 0 && (size_t)half < N;
+  if (direct && b->host_zero_copy && !b->subset) {
+    mjb_buffers Bh = b->B;
+    void *d_obs = nullptr, *d_rew = nullptr, *d_term = nullptr, *d_trunc = nullptr;
+    if (cudaHostGetDevicePointer(&d_obs, obs, 0) == cudaSuccess && cudaHostGetDevicePointer(&d_rew, reward, 0) == cudaSuccess &&
+        cudaHostGetDevicePointer(&d_term, term, 0) == cudaSuccess && cudaHostGetDevicePointer(&d_trunc, trunc, 0) == cudaSuccess) {
+      Bh.obs = (float*)d_obs; Bh.reward = (float*)d_rew; Bh.term = (uint8_t*)d_term; Bh.trunc = (uint8_t*)d_trunc;
+      const size_t act_row = sizeof(float) * A * dm.act_stride;
+      if (split) {
+        CUDA_TRY(cudaEventRecord(b->ev_fork, b->stream));
+        CUDA_TRY(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
+        CUDA_TRY(cudaMemcpyAsync(b->B.actions, actions, act_row * half, cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaMemcpyAsync((char*)b->B.actions + act_row * half, (const char*)actions + act_row * half, act_row * (N - half),
+                                 cudaMemcpyHostToDevice, b->stream2));
+        int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr, b->stream, 0, half, &Bh);
+        if (rc != MJB_OK) return rc;
+        rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr, b->stream2, half, (int)N - half, &Bh);
+        if (rc != MJB_OK) return rc;
+        CUDA_TRY(cudaEventRecord(b->ev_join, b->stream2));
+        CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
+      } else {
+        CUDA_TRY(cudaMemcpyAsync(b->B.actions, actions, nb_act, cudaMemcpyHostToDevice, b->stream));
+        int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr, b->stream, 0, -1, &Bh);
+        if (rc != MJB_OK) return rc;
+      }
+      CUDA_TRY(cudaStreamSynchronize(b->stream));
+      return MJB_OK;
+    }
+    cudaGetLastError();   // not device-addressable after all: fall through to the copying paths
+  }
+  // Two halves on two streams: the second half's actions go up while the first half computes, and the first
+  // half's observations come down while the second half computes.
+  if (split && packed_out) {
     const size_t act_row = sizeof(float) * A * dm.act_stride, obs_row = sizeof(float) * A * dm.obs_stride;
     CUDA_TRY(cudaEventRecord(b->ev_fork, b->stream));
     CUDA_TRY(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
