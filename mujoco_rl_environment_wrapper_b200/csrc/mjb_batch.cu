@@ -46,8 +46,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// One CTA per SM slot, `warps` environments in flight per CTA; each warp walks the env index space
-// with a grid-wide stride (envs are independent, no inter-warp communication after the staging).
+// One CTA per SM, `warps` environments in flight per CTA; each warp walks the env index space with a grid-wide
+// stride (envs are independent: the warps only meet at the staging of the model image and at the round barrier).
+// `active` envs are walked starting at `env_base` (range launches of the host-buffer step) or through `env_order`
+// (a scheduling permutation, or the env ids of one level: mjb_set_env_subset).
 template <bool PHYS, bool PACKED>
 __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_env(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
                       int num_envs, int mode, int skip_frames, const uint8_t* __restrict__ mask, int* __restrict__ next_env,
@@ -71,8 +73,6 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
   Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1};
-  // dynamic env scheduling: per-env cost varies (contact count, Newton iterations), so every warp pulls
-  // its next env from a grid-wide counter instead of owning a fixed slice
   // Two scheduling modes share ONE call site of the step code:
   //  * lock-step rounds (default): every env-warp of the CTA takes one env per round and the CTA re-aligns
   //    at each round boundary, so the warps walk through the (large) step code together and share
