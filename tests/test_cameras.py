@@ -204,3 +204,16 @@ def test_cameras_follow_each_envs_level(tmp_path):
     for e in range(16):
         assert np.array_equal(got[e], want[lid[e]][e]), e
     assert not np.array_equal(want[0], want[1]), "the changed box must be visible to some camera"
+
+
+def test_oracle_reproduces_committed_camera_fixture():
+    """tests/golden/camera_two_ants.npz: both agent cameras of the two-ant level at a stored state, written by the
+    oracle (the script is this test's body run with np.savez).  Guards the image formation against silent changes."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "camera_two_ants.npz"))
+    m = L.Model(open(os.path.join(LV, "two_ants_cams.xml")).read())
+    s = OracleSim(m.blob)
+    s.array("qpos")[:] = g["qpos"]
+    s.forward()
+    imgs = np.stack([s.render(k, 64, 64) for k in range(2)])
+    assert np.array_equal(imgs, g["images"])
+    assert 0.3 < (imgs.sum(axis=-1) > 0).mean() < 0.9   # floor below the horizon, sky above
