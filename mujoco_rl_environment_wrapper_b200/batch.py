@@ -107,9 +107,14 @@ class Batch:
             self._subset = None
             L.check(self._lib.mjb_set_env_subset(self._h, None, 0), "env subset")
             return
-        self._subset = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
-        L.check(self._lib.mjb_set_env_subset(self._h, ctypes.c_void_p(self._subset.data_ptr()), int(self._subset.numel())),
-                "env subset")
+        ids = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        count = int(ids.numel())
+        if count == 0:
+            # a zero-element tensor has data_ptr() == 0, and NULL means "all envs" to the C side: an empty level
+            # must stay empty, so hand over a valid one-element dummy with count = 0
+            ids = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._subset = ids
+        L.check(self._lib.mjb_set_env_subset(self._h, ctypes.c_void_p(self._subset.data_ptr()), count), "env subset")
 
     def render(self, cam_ids, width=64, height=64, out=None):
         """u8 [num_envs, len(cam_ids), height, width, 3] images of the listed fixed cameras at the current qpos

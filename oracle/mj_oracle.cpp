@@ -25,11 +25,14 @@
 #include <cstring>
 #include <vector>
 
-#include "../mujoco_rl_environment_wrapper_b200/csrc/hmath.h"
-#include "../mujoco_rl_environment_wrapper_b200/csrc/host_kin.h"
-#include "../mujoco_rl_environment_wrapper_b200/csrc/model_view.h"
+// No product source is included: the oracle's own linear algebra, blob reader, kinematics, Jacobians and
+// mass matrix live in orc_base.h; the only shared artefact is the PUBLIC blob format (include/mjb_blob.h),
+// whose every field is pinned by an independent derivation from the XML (oracle/model_ref.py,
+// tests/test_model_constants.py).
+#include "orc_base.h"
 
-using namespace mjb;
+using namespace orc;
+using ModelView = orc::Model;
 
 namespace {
 
@@ -51,7 +54,7 @@ struct Sim {
   std::vector<double> qpos, qvel, ctrl, qacc, qacc_warmstart, qacc_smooth, qfrc_smooth, qfrc_bias, qfrc_passive,
       qfrc_actuator, qfrc_constraint, sensordata;
   double time = 0;
-  HostKin kin;
+  Kin kin;
   std::vector<double> xpos, xmat, xipos, geom_xpos, geom_xmat, site_xpos, site_xmat;  // flat mirrors for the API
   std::vector<double> M, L;                                                             // dense mass matrix, Cholesky
   std::vector<Contact> contacts;
@@ -84,7 +87,7 @@ void kinematics(Sim& s) {
       if (n < kMinVal) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
       else if (std::fabs(n - 1) > kMinVal) for (int i = 0; i < 4; i++) q[i] /= n;
     }
-  host_fk(m, s.qpos.data(), s.kin);
+  forward_kinematics(m, s.qpos.data(), s.kin);
   for (int b = 0; b < m.nbody; b++) {
     for (int i = 0; i < 3; i++) { s.xpos[3 * b + i] = s.kin.xpos[b][i]; s.xipos[3 * b + i] = s.kin.xipos[b][i]; }
     for (int i = 0; i < 9; i++) s.xmat[9 * b + i] = s.kin.xmat[b].m[i];
@@ -92,14 +95,14 @@ void kinematics(Sim& s) {
   for (int g = 0; g < m.ngeom; g++) {
     int b = m.geom_bodyid[g];
     V3 p = s.kin.xpos[b] + mulv(s.kin.xmat[b], V3(m.geom_pos[3 * g], m.geom_pos[3 * g + 1], m.geom_pos[3 * g + 2]));
-    M3 R = q2m(qmul(s.kin.xquat[b], Quat{m.geom_quat[4 * g], m.geom_quat[4 * g + 1], m.geom_quat[4 * g + 2], m.geom_quat[4 * g + 3]}));
+    M3 R = mul(s.kin.xmat[b], rot_from_quat(m.geom_quat + 4 * g));
     for (int i = 0; i < 3; i++) s.geom_xpos[3 * g + i] = p[i];
     for (int i = 0; i < 9; i++) s.geom_xmat[9 * g + i] = R.m[i];
   }
   for (int t = 0; t < m.nsite; t++) {
     int b = m.site_bodyid[t];
     V3 p = s.kin.xpos[b] + mulv(s.kin.xmat[b], V3(m.site_pos[3 * t], m.site_pos[3 * t + 1], m.site_pos[3 * t + 2]));
-    M3 R = q2m(qmul(s.kin.xquat[b], Quat{m.site_quat[4 * t], m.site_quat[4 * t + 1], m.site_quat[4 * t + 2], m.site_quat[4 * t + 3]}));
+    M3 R = mul(s.kin.xmat[b], rot_from_quat(m.site_quat + 4 * t));
     for (int i = 0; i < 3; i++) s.site_xpos[3 * t + i] = p[i];
     for (int i = 0; i < 9; i++) s.site_xmat[9 * t + i] = R.m[i];
   }
@@ -505,8 +508,8 @@ void make_constraints(Sim& s) {
     Contact& c = s.contacts[ci];
     c.efc_address = s.nefc;
     int b1 = m.geom_bodyid[c.g1], b2 = m.geom_bodyid[c.g2];
-    host_jac(m, s.kin, b1, c.pos, jp1, jr1);
-    host_jac(m, s.kin, b2, c.pos, jp2, jr2);
+    point_jacobian(m, s.kin, b1, c.pos, jp1, jr1);
+    point_jacobian(m, s.kin, b2, c.pos, jp2, jr2);
     std::vector<double> jn(nv), jt1(nv), jt2(nv);
     for (int d = 0; d < nv; d++) {
       V3 dif(jp2[d] - jp1[d], jp2[nv + d] - jp1[nv + d], jp2[2 * nv + d] - jp1[2 * nv + d]);
@@ -626,9 +629,9 @@ void solve_newton(Sim& s, bool fixed_iters) {
     double gn = 0;
     for (int i = 0; i < nv; i++) gn += grad[i] * grad[i];
     if (!fixed_iters && std::sqrt(gn) < 1e-11) break;
-    if (!host_cholesky(H, nv)) break;
+    if (!cholesky(H, nv)) break;
     for (int i = 0; i < nv; i++) sv[i] = -grad[i];
-    host_chol_solve(H, nv, sv.data());
+    cholesky_solve(H, nv, sv.data());
     for (int r = 0; r < ne; r++) {
       double x = 0;
       for (int d = 0; d < nv; d++) x += s.J[(size_t)r * nv + d] * sv[d];
@@ -661,7 +664,7 @@ void solve_pgs(Sim& s, bool fixed_iters) {
   std::vector<double> MinvJt((size_t)ne * nv), AR((size_t)ne * ne), b(ne);
   for (int r = 0; r < ne; r++) {
     std::vector<double> x(s.J.begin() + (size_t)r * nv, s.J.begin() + (size_t)(r + 1) * nv);
-    host_chol_solve(s.L, nv, x.data());
+    cholesky_solve(s.L, nv, x.data());
     for (int d = 0; d < nv; d++) MinvJt[(size_t)r * nv + d] = x[d];
   }
   for (int r = 0; r < ne; r++) {
@@ -864,9 +867,9 @@ void forward(Sim& s, bool with_sensors) {
   const ModelView& m = *s.m;
   int nv = m.nv;
   kinematics(s);
-  host_mass_matrix(m, s.kin, s.M);
+  mass_matrix(m, s.kin, s.M);
   s.L = s.M;
-  host_cholesky(s.L, nv);
+  cholesky(s.L, nv);
   collision(s);
   if (with_sensors) sensors_pos(s);
   // velocity-dependent terms
@@ -880,7 +883,7 @@ void forward(Sim& s, bool with_sensors) {
   }
   for (int d = 0; d < nv; d++) s.qfrc_smooth[d] = s.qfrc_passive[d] - s.qfrc_bias[d] + s.qfrc_actuator[d];
   s.qacc_smooth = s.qfrc_smooth;
-  host_chol_solve(s.L, nv, s.qacc_smooth.data());
+  cholesky_solve(s.L, nv, s.qacc_smooth.data());
   make_constraints(s);
   if (s.nefc == 0) {
     s.qacc = s.qacc_smooth;
@@ -901,12 +904,14 @@ void integrate_pos(const ModelView& m, std::vector<double>& qpos, const double* 
       for (int i = 0; i < 3; i++) qpos[qa + i] += h * qvel[da + i];
       V3 w(qvel[da + 3], qvel[da + 4], qvel[da + 5]);
       double ang = norm(w) * h;
-      Quat q{qpos[qa + 3], qpos[qa + 4], qpos[qa + 5], qpos[qa + 6]};
       if (ang > 0) {
-        Quat dq = qaxisangle(normalized(w), ang);
-        q = qnormalized(qmul(q, dq));
+        // q <- q * exp(w h / 2): the angular velocity of a free joint is expressed in the body frame
+        V3 u = normalized(w);
+        double sn = std::sin(0.5 * ang), dq[4] = {std::cos(0.5 * ang), u.x * sn, u.y * sn, u.z * sn}, out[4];
+        quat_mul(&qpos[qa + 3], dq, out);
+        double nn = std::sqrt(out[0] * out[0] + out[1] * out[1] + out[2] * out[2] + out[3] * out[3]);
+        for (int i = 0; i < 4; i++) qpos[qa + 3 + i] = out[i] / nn;
       }
-      qpos[qa + 3] = q.w; qpos[qa + 4] = q.x; qpos[qa + 5] = q.y; qpos[qa + 6] = q.z;
     } else {
       qpos[qa] += h * qvel[da];
     }
@@ -924,9 +929,9 @@ void euler(Sim& s) {
     // implicit-in-velocity joint damping: (M + h D) a' = qfrc_smooth + qfrc_constraint
     std::vector<double> A = s.M;
     for (int d = 0; d < nv; d++) A[(size_t)d * nv + d] += h * m.dof_damping[d];
-    host_cholesky(A, nv);
+    cholesky(A, nv);
     for (int d = 0; d < nv; d++) qacc[d] = s.qfrc_smooth[d] + s.qfrc_constraint[d];
-    host_chol_solve(A, nv, qacc.data());
+    cholesky_solve(A, nv, qacc.data());
   }
   for (int d = 0; d < nv; d++) s.qvel[d] += h * qacc[d];
   integrate_pos(m, s.qpos, s.qvel.data(), h);
@@ -1064,7 +1069,7 @@ int orc_render(void* p, int cam, int width, int height, uint8_t* out) {
   kinematics(*s);
   const int b = m.cam_bodyid[cam];
   V3 o = s->kin.xpos[b] + mulv(s->kin.xmat[b], V3(m.cam_pos[3 * cam], m.cam_pos[3 * cam + 1], m.cam_pos[3 * cam + 2]));
-  M3 R = q2m(qmul(s->kin.xquat[b], Quat{m.cam_quat[4 * cam], m.cam_quat[4 * cam + 1], m.cam_quat[4 * cam + 2], m.cam_quat[4 * cam + 3]}));
+  M3 R = mul(s->kin.xmat[b], rot_from_quat(m.cam_quat + 4 * cam));
   const double th = std::tan(0.5 * m.cam_fovy[cam] * 3.14159265358979323846 / 180.0), aspect = (double)width / height;
   const double ambient = 0.4, diffuse = 0.6;
   for (int iy = 0; iy < height; iy++)
@@ -1110,7 +1115,7 @@ double orc_energy(void* p) {
   Sim* s = (Sim*)p;
   const ModelView& m = *s->m;
   kinematics(*s);
-  host_mass_matrix(m, s->kin, s->M);
+  mass_matrix(m, s->kin, s->M);
   double ke = 0, pe = 0;
   for (int i = 0; i < m.nv; i++)
     for (int j = 0; j < m.nv; j++) ke += 0.5 * s->qvel[i] * s->M[(size_t)i * m.nv + j] * s->qvel[j];

@@ -21,8 +21,8 @@ def oracle_lib_path():
 def build_oracle(force=False):
     """Compile the oracle with g++ (a few seconds). Building the checker is not using it."""
     path = oracle_lib_path()
-    src = os.path.join(_HERE, "mj_oracle.cpp")
-    if force or not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("mj_oracle.cpp", "orc_base.h", "orc_collide.h") if os.path.exists(os.path.join(_HERE, f))]
+    if force or not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return path
 

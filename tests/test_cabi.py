@@ -64,3 +64,14 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text and "mj_oracle" not in text, f
+
+
+def test_oracle_includes_no_product_source():
+    """the checker must stay independent of the thing it checks: oracle/ may include the public blob format
+    (include/mjb_blob.h) and nothing from the package (csrc/)"""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, "oracle", "*.cpp")) + glob.glob(os.path.join(root, "oracle", "*.h")):
+        for inc in re.findall(r'#include\s+"([^"]+)"', open(path).read()):
+            assert "csrc" not in inc and "mujoco_rl_environment_wrapper_b200" not in inc, (path, inc)

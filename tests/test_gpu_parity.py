@@ -560,6 +560,22 @@ def test_level_variants_single_env_follows_reference_draw(tmp_path):
         obs, *_ = env.step({a: env.action_space(a).sample() for a in env.agents})
         assert obs["sender"].shape == (59,)
     assert seen == expect and len(set(seen)) == 2
+    # a level that currently owns NO env must not step / reset the env with its model (an empty id list used to
+    # reach the C side as NULL = "all envs": two steps per step(), obs from the wrong level)
+    singles = {xa: MuJoCoRL({"xmlPath": xa, "infoJson": ja, "agents": ["sender", "receiver"]}),
+               xb: MuJoCoRL({"xmlPath": xb, "infoJson": jb, "agents": ["sender", "receiver"]})}
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        env.reset()
+        ref = singles[env.xml_path]
+        ref.reset()
+        for t in range(6):
+            act = {a: rng.uniform(-1, 1, 8).astype(np.float32) for a in env.agents}
+            o1, *_ = env.step(act)
+            o2, *_ = ref.step(act)
+            assert int(env.batch.timestep[0]) == t + 1 == int(ref.batch.timestep[0])
+            assert torch.equal(env.batch.qpos, ref.batch.qpos) and torch.equal(env.batch.qvel, ref.batch.qvel)
+            assert np.array_equal(o1["sender"], o2["sender"]) and np.array_equal(o1["receiver"], o2["receiver"])
 
 
 @pytest.mark.gpu
