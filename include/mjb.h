@@ -152,6 +152,8 @@ typedef struct mjb_buffers {
   int32_t* niter;        /* [N] or NULL: Newton iterations of the last forward pass (diagnostic) */
   int32_t* nreset;       /* [N] or NULL: how often the env was auto-reset because its state became non-finite
                             (MuJoCo's mj_checkPos / mj_checkVel behaviour: warn and mj_resetData) */
+  int32_t* ncon_dropped; /* [N] or NULL: cumulative count of contacts found beyond the env's `maxcon` slots and
+                            therefore dropped (MuJoCo grows its arena instead); 0 = every contact was simulated */
 } mjb_buffers;
 
 /* data_store column ids */

@@ -58,7 +58,7 @@ class Layout(ctypes.Structure):
 class Buffers(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("qpos", "qvel", "ctrl", "warmstart", "sensordata", "probe", "actions", "obs", "reward", "term",
-                 "trunc", "timestep", "store_i", "store_f", "ncon", "contact_geom", "contact_dist", "niter", "nreset")]
+                 "trunc", "timestep", "store_i", "store_f", "ncon", "contact_geom", "contact_dist", "niter", "nreset", "ncon_dropped")]
 
 
 _LIB = None

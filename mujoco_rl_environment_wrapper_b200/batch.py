@@ -51,7 +51,7 @@ class Batch:
             "reward": view(1, f32, (N, max(1, A))), "term": view(2, u8, (N, A + 1)), "trunc": view(3, u8, (N, A + 1)),
             "timestep": z((N,), i32), "store_i": z((N, max(1, A), lay.store_i32), i32),
             "store_f": z((N, max(1, A), lay.store_f32), f32), "ncon": z((N,), i32),
-            "contact_geom": z((N, lay.maxcon, 2), i32), "contact_dist": z((N, lay.maxcon), f32), "niter": z((N,), i32), "nreset": z((N,), i32),
+            "contact_geom": z((N, lay.maxcon, 2), i32), "contact_dist": z((N, lay.maxcon), f32), "niter": z((N,), i32), "nreset": z((N,), i32), "ncon_dropped": z((N,), i32),
         }
         B = L.Buffers()
         for k, v in self.buf.items():

@@ -587,7 +587,7 @@ inline int choose_pack(const HostModel& host, const mjb_env_spec& spec, int num_
   int K = 32 / std::max(1, nv);
   if (spec.n_agents > 0) K = std::min(K, MJB_MAX_AGENTS / spec.n_agents);
   if (spec.n_targets > 0) K = std::min(K, MJB_MAX_TARGETS / spec.n_targets);
-  K = std::min(K, env_int("MJB_PACK", 4));
+  K = std::min(K, std::min(4, env_int("MJB_PACK", 4)));   // 4 = MJB_MAX_PACK (per-copy contact quotas in step_kernel.cuh)
   K = std::min(K, num_envs);
   if (spec.skip_frames == 0) K = 1;   // no physics in the step: nothing to share
   if (spec.flags & MJB_SPEC_NO_PACK) K = 1;

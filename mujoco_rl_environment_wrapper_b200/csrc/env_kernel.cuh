@@ -304,7 +304,13 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
   int niter = 0;
   if (PHYS) {
     MJB_NOUNROLL
-    for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, &niter);
+    int dropped[MJB_MAX_PACK] = {0, 0, 0, 0};
+    for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, &niter, dropped);
+    if (B.ncon_dropped && lane == 0) {   // cumulative per real env: stays 0 while no contact was ever dropped
+#pragma unroll
+      for (int k = 0; k < MJB_MAX_PACK; k++)
+        if (k < K && dropped[k] && ((upd >> k) & 1u)) B.ncon_dropped[e0 + k] += dropped[k];
+    }
     if (integrate) {
       // MuJoCo's mj_checkPos / mj_checkVel: a non-finite or absurd state resets that env (here: that copy)
       MJB_NOUNROLL

@@ -21,6 +21,7 @@
 namespace mjb {
 
 #define MJB_MINVAL 1e-15f
+#define MJB_MAX_PACK 4   // real envs per warp at most (replicate.h, choose_pack)
 #define MJB_BIG 1e30f
 
 struct f3 { float x, y, z; };
@@ -400,30 +401,53 @@ MJB_DEV float point_box_dist(f3 p, const float* size) {
   float s2 = (ex > 0 ? ex * ex : 0.f) + (ey > 0 ? ey * ey : 0.f) + (ez > 0 ? ez * ez : 0.f);
   return s2 > 0 ? sqrtf(s2) : fmaxf(ex, fmaxf(ey, ez));
 }
+// capsule - box (specification: DESIGN.md 3c; the fp64 checker finds the same minimiser exactly, by breakpoints).
+//   1. t* = argmin over the capsule axis p(t) = c + t d, t in [-1, 1], of the signed distance to the box
+//      (convex in t: golden-section search, then compared with the two ends);
+//   2. inside the box: one sphere there;
+//   3. else k = dominant axis of (p* - closest box point) = the closest FACE, I = the part of the segment whose
+//      projection lies in that face's rectangle; t* in I (within 0.05): spheres at the two ends of I, deeper
+//      first (ends closer than 1e-3 count once); otherwise one sphere at t*.
+// Every sphere goes through sphere - box with the pair's margin.
 MJB_DEV int capsule_box(const GeomW& g1, const GeomW& g2, float margin, ConOut* o) {
-  float r = g1.size[0], h = g1.size[1];
-  f3 ax = colv(g1.mat, 2);
-  f3 a = mulTv(g2.mat, g1.pos - ax * h - g2.pos), b = mulTv(g2.mat, g1.pos + ax * h - g2.pos);
-  f3 ab = b - a;
-  float lo = 0.f, hi = 1.f;
+  const float r = g1.size[0], h = g1.size[1];
+  const f3 ax = colv(g1.mat, 2);
+  const f3 c = mulTv(g2.mat, g1.pos - g2.pos), d = mulTv(g2.mat, ax) * h;
+  float lo = -1.f, hi = 1.f;
   const float gr = 0.6180339887f;
   float x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
-  float f1 = point_box_dist(a + ab * x1, g2.size), f2 = point_box_dist(a + ab * x2, g2.size);
+  float f1 = point_box_dist(c + d * x1, g2.size), f2 = point_box_dist(c + d * x2, g2.size);
   MJB_NOUNROLL
   for (int it = 0; it < 40; it++) {
-    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = point_box_dist(a + ab * x1, g2.size); }
-    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = point_box_dist(a + ab * x2, g2.size); }
+    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = point_box_dist(c + d * x1, g2.size); }
+    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = point_box_dist(c + d * x2, g2.size); }
   }
-  float tm = 0.5f * (lo + hi), dmid = point_box_dist(a + ab * tm, g2.size);
-  float d0 = point_box_dist(a, g2.size), d1 = point_box_dist(b, g2.size);
-  int n = 0;
-  if (fminf(d0, d1) <= dmid + 1e-6f) {
-    float t0 = d1 < d0 ? 1.f : 0.f;
-    n += sphere_box(g1.pos + ax * ((2 * t0 - 1) * h), r, g2.pos, g2.mat, g2.size, margin, o[n]);
-    n += sphere_box(g1.pos + ax * ((1 - 2 * t0) * h), r, g2.pos, g2.mat, g2.size, margin, o[n]);
-  } else {
-    n += sphere_box(g1.pos + ax * ((2 * tm - 1) * h), r, g2.pos, g2.mat, g2.size, margin, o[n]);
+  float ts = 0.5f * (lo + hi), best = point_box_dist(c + d * ts, g2.size);
+  const float fm = point_box_dist(c - d, g2.size), fp = point_box_dist(c + d, g2.size);
+  if (fm <= best) { best = fm; ts = -1.f; }
+  if (fp < best) { best = fp; ts = 1.f; }
+  if (best > margin + r) return 0;
+  if (best <= 0.f) return sphere_box(g1.pos + ax * (ts * h), r, g2.pos, g2.mat, g2.size, margin, o[0]);
+  const f3 p = c + d * ts;
+  const float sx = fabsf(p.x - fminf(g2.size[0], fmaxf(-g2.size[0], p.x))), sy = fabsf(p.y - fminf(g2.size[1], fmaxf(-g2.size[1], p.y))),
+              sz = fabsf(p.z - fminf(g2.size[2], fmaxf(-g2.size[2], p.z)));
+  int kf = 0;
+  if (sy > sx) kf = 1;
+  if (sz > (kf ? sy : sx)) kf = 2;
+  float tl = -1.f, th = 1.f;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    if (j == kf) continue;
+    const float cj = comp(c, j), dj = comp(d, j), sj = g2.size[j];
+    if (fabsf(dj) < 1e-12f) { if (fabsf(cj) > sj) { tl = 1.f; th = -1.f; } continue; }
+    const float inv = 1.f / dj, t0 = (-sj - cj) * inv, t1 = (sj - cj) * inv;
+    tl = fmaxf(tl, fminf(t0, t1)); th = fminf(th, fmaxf(t0, t1));
   }
+  if (tl > th || ts < tl - 0.05f || ts > th + 0.05f) return sphere_box(g1.pos + ax * (ts * h), r, g2.pos, g2.mat, g2.size, margin, o[0]);
+  const bool lo_first = point_box_dist(c + d * tl, g2.size) <= point_box_dist(c + d * th, g2.size);
+  const float ta = lo_first ? tl : th, tb = lo_first ? th : tl;
+  int n = sphere_box(g1.pos + ax * (ta * h), r, g2.pos, g2.mat, g2.size, margin, o[0]);
+  if (th - tl > 1e-3f) n += sphere_box(g1.pos + ax * (tb * h), r, g2.pos, g2.mat, g2.size, margin, o[n]);
   return n;
 }
 MJB_DEV int capsule_capsule(const GeomW& g1, const GeomW& g2, float margin, ConOut* o) {
@@ -454,6 +478,120 @@ MJB_DEV int capsule_capsule(const GeomW& g1, const GeomW& g2, float margin, ConO
   return k;
 }
 
+// box - box, one pair per call, the whole warp cooperating (specification: DESIGN.md 3c; the fp64 checker clips the
+// incident face sequentially, Sutherland - Hodgman).  Lanes 0..14 evaluate the 15 separating axes; the contact axis is
+// the face axis of largest separation unless an edge axis beats it by 5 % + 1e-6.  Face contact: the vertices of
+// (incident face) n (reference rectangle) are enumerated in parallel — lanes 0..3 incident vertices inside the
+// rectangle, 4..7 rectangle corners strictly inside the incident quad, 8..23 incident edge x rectangle side
+// crossings — and kept when within `margin` of the reference plane.  Edge contact: lane 0, closest points of the two
+// supporting edges.  Returns whether this lane holds a contact (at most 8 lanes do).
+MJB_DEV bool box_box_lane(int lane, const GeomW& a, const GeomW& b, float margin, ConOut& o) {
+  const f3 dc = b.pos - a.pos;
+  float sp = -MJB_BIG;
+  bool valid = false;
+  if (lane < 15) {
+    f3 L;
+    if (lane < 3) { L = colv(a.mat, lane); valid = true; }
+    else if (lane < 6) { L = colv(b.mat, lane - 3); valid = true; }
+    else {
+      const int e = lane - 6, i = e / 3, j = e - 3 * i;
+      L = cross(colv(a.mat, i), colv(b.mat, j));
+      const float len = sqrtf(dot(L, L));
+      valid = len >= 1e-6f;
+      L = L * (1.f / fmaxf(len, 1e-12f));
+    }
+    const f3 la = mulTv(a.mat, L), lb = mulTv(b.mat, L);
+    sp = fabsf(dot(L, dc)) - (a.size[0] * fabsf(la.x) + a.size[1] * fabsf(la.y) + a.size[2] * fabsf(la.z)) -
+         (b.size[0] * fabsf(lb.x) + b.size[1] * fabsf(lb.y) + b.size[2] * fabsf(lb.z));
+  }
+  if (MJB_BALLOT(valid && sp > margin)) return false;
+  const float fsep = wmax(lane < 6 ? sp : -MJB_BIG), esep = wmax((lane >= 6 && valid) ? sp : -MJB_BIG);
+  const int fax = MJB_FFS(MJB_BALLOT(lane < 6 && sp == fsep)) - 1;
+  const int eax = MJB_FFS(MJB_BALLOT(lane >= 6 && valid && sp == esep)) - 7;   // -7 + ... : < 0 when no edge axis is valid
+  o.t = mk3(0, 0, 0);
+  if (eax >= 0 && esep > fsep + 0.05f * fabsf(fsep) + 1e-6f) {
+    if (lane != 0) return false;
+    const int i = eax / 3, j = eax - 3 * i;
+    const f3 u = colv(a.mat, i), v = colv(b.mat, j);
+    f3 L = cross(u, v);
+    L = L * (1.f / sqrtf(dot(L, L)));
+    if (dot(L, dc) < 0.f) L = L * -1.f;
+    f3 pa = a.pos, pb = b.pos;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const f3 ak = colv(a.mat, k), bk = colv(b.mat, k);
+      if (k != i) pa = pa + ak * (a.size[k] * (dot(L, ak) >= 0.f ? 1.f : -1.f));
+      if (k != j) pb = pb - bk * (b.size[k] * (dot(L, bk) >= 0.f ? 1.f : -1.f));
+    }
+    const f3 w = pa - pb;
+    const float uv = dot(u, v), den = 1.f - uv * uv, uw = dot(u, w), vw = dot(v, w);
+    float ta = (uv * vw - uw) / den, tb = (vw - uv * uw) / den;
+    ta = fminf(a.size[i], fmaxf(-a.size[i], ta)); tb = fminf(b.size[j], fmaxf(-b.size[j], tb));
+    o.dist = esep; o.pos = (pa + u * ta + pb + v * tb) * 0.5f; o.n = L;
+    return true;
+  }
+  // face contact: A = the box owning the axis (reference), B = the other (incident)
+  const bool ref1 = fax < 3;
+  const int ri = ref1 ? fax : fax - 3;
+  const GeomW& A = ref1 ? a : b;
+  const GeomW& B = ref1 ? b : a;
+  f3 nA = colv(A.mat, ri);
+  if (dot(nA, B.pos - A.pos) < 0.f) nA = nA * -1.f;
+  const f3 nb = mulTv(B.mat, nA);   // nA in B's axes
+  int bj = 0;
+  if (fabsf(nb.y) > fabsf(nb.x)) bj = 1;
+  if (fabsf(nb.z) > fabsf(comp(nb, bj))) bj = 2;
+  const f3 mB = colv(B.mat, bj) * (comp(nb, bj) > 0.f ? -1.f : 1.f);
+  const int bu = bj == 2 ? 0 : bj + 1, bw = bu == 2 ? 0 : bu + 1, au = ri == 2 ? 0 : ri + 1, aw = au == 2 ? 0 : au + 1;
+  const f3 Bu = colv(B.mat, bu) * B.size[bu], Bw = colv(B.mat, bw) * B.size[bw], Au = colv(A.mat, au), Aw = colv(A.mat, aw);
+  const f3 fc = B.pos + mB * B.size[bj];            // centre of the incident face
+  const float su = A.size[au], sw = A.size[aw];
+  // corner q of a quad in the order (+,+), (-,+), (-,-), (+,-)
+  auto s0 = [](int q) { return (q == 0 || q == 3) ? 1.f : -1.f; };
+  auto s1 = [](int q) { return q < 2 ? 1.f : -1.f; };
+  bool hit = false;
+  f3 x = mk3(0, 0, 0);
+  if (lane < 4) {
+    x = fc + Bu * s0(lane) + Bw * s1(lane);
+    const f3 rel = x - A.pos;
+    hit = fabsf(dot(rel, Au)) <= su && fabsf(dot(rel, Aw)) <= sw;
+  } else if (lane < 8) {
+    const int q = lane - 4;
+    const float U = s0(q) * su, W = s1(q) * sw;
+    // strictly inside the projected incident quad: same side of all four edges
+    int pos_ = 0, neg_ = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const f3 p0 = fc + Bu * s0(e) + Bw * s1(e) - A.pos, p1 = fc + Bu * s0((e + 1) & 3) + Bw * s1((e + 1) & 3) - A.pos;
+      const float u0 = dot(p0, Au), w0 = dot(p0, Aw), u1 = dot(p1, Au), w1 = dot(p1, Aw);
+      const float cr = (u1 - u0) * (W - w0) - (w1 - w0) * (U - u0);
+      pos_ += cr > 0.f; neg_ += cr < 0.f;
+    }
+    if (pos_ == 4 || neg_ == 4) {
+      const f3 x0 = A.pos + nA * A.size[ri] + Au * U + Aw * W;
+      const float t = dot(mB, fc - x0) / dot(mB, nA);   // |mB . nA| >= 1 / sqrt(3): the most anti-parallel face
+      x = x0 + nA * t;
+      hit = true;
+    }
+  } else if (lane < 24) {
+    const int e = (lane - 8) >> 2, side = (lane - 8) & 3;
+    const f3 p0 = fc + Bu * s0(e) + Bw * s1(e), p1 = fc + Bu * s0((e + 1) & 3) + Bw * s1((e + 1) & 3);
+    const f3 ax_ = side < 2 ? Au : Aw, ot_ = side < 2 ? Aw : Au;
+    const float sg = (side & 1) ? -1.f : 1.f, lim_ = side < 2 ? su : sw, olim = side < 2 ? sw : su;
+    const float f0 = sg * dot(p0 - A.pos, ax_) - lim_, f1 = sg * dot(p1 - A.pos, ax_) - lim_;
+    if ((f0 < 0.f && f1 > 0.f) || (f0 > 0.f && f1 < 0.f)) {
+      x = p0 + (p1 - p0) * (f0 / (f0 - f1));
+      hit = fabsf(dot(x - A.pos, ot_)) <= olim;
+    }
+  }
+  if (hit) {
+    const float dist = dot(x - A.pos, nA) - A.size[ri];
+    if (dist > margin) hit = false;
+    o.dist = dist; o.pos = x - nA * (0.5f * dist); o.n = ref1 ? nA : nA * -1.f;
+  }
+  return hit;
+}
+
 MJB_DEV void make_frame(f3 n, f3 t, float* fr) {
   float nn = sqrtf(dot(n, n));
   n = n * (1.0f / nn);
@@ -476,8 +614,9 @@ MJB_DEV void store_contact(const Ctx& c, int idx, const ConOut& o, int pair, flo
   r[CON_MU] = mu;
 }
 
-// returns the number of contacts (warp-uniform); fills SF_con
-MJB_DEV int collide(const Ctx& c) {
+// returns the number of contacts stored (warp-uniform); fills SF_con.  `tot[copy]` is ADVANCED by the number of
+// contacts found for that copy of a packed env (pack == 1: tot[0]) before the per-copy quota of maxcon1 slots
+MJB_DEV int collide(const Ctx& c, int* tot) {
   const DevModel& dm = *c.dm;
   const uint32_t* pairs = CU(pair_pack);
   int* cand = SI(cand);
@@ -581,10 +720,23 @@ MJB_DEV int collide(const Ctx& c) {
         else if (b.type == MJB_GEOM_BOX) n = capsule_box(a, b, margin, o);
       }
     }
+    // append in candidate order; every copy of a packed env has its own quota of maxcon1 slots (a contact-heavy
+    // copy must not starve its neighbours), `tot` counts what was found so that dropped contacts are visible
+    const int copy = (dm.pack > 1 && p >= 0) ? (int)(pairs[p] & 0xfff) / dm.ngeom1 : 0;
+    const uint32_t lt = (1u << c.lane) - 1u;
     for (int k = 0; k < 2; k++) {
-      uint32_t bal = MJB_BALLOT(n > k);
-      int idx = ncon + MJB_POPC(bal & ((1u << c.lane) - 1u));
-      if (n > k && idx < dm.maxcon) store_contact(c, idx, o[k], p, mu);
+      const bool has = n > k;
+      bool acc = has;
+#pragma unroll
+      for (int cp = 0; cp < MJB_MAX_PACK; cp++) {
+        if (cp < dm.pack) {   // warp-uniform
+          const uint32_t bc = MJB_BALLOT(has && copy == cp);
+          if (has && copy == cp && tot[cp] + MJB_POPC(bc & lt) >= dm.maxcon1) acc = false;
+          tot[cp] += MJB_POPC(bc);
+        }
+      }
+      const uint32_t bal = MJB_BALLOT(acc);
+      if (acc) store_contact(c, ncon + MJB_POPC(bal & lt), o[k], p, mu);
       ncon += MJB_POPC(bal);
     }
   }
@@ -616,32 +768,22 @@ MJB_DEV int collide(const Ctx& c) {
       }
     } else {
       lim = 8;
-      if (c.lane < 16) {
-        int pass = c.lane >> 3, ci = c.lane & 7;
-        const GeomW& A = pass == 0 ? a : b; const GeomW& B = pass == 0 ? b : a;
-        f3 vec = mk3(A.size[0] * ((ci & 1) ? 1.f : -1.f), A.size[1] * ((ci & 2) ? 1.f : -1.f), A.size[2] * ((ci & 4) ? 1.f : -1.f));
-        f3 pw = A.pos + mulv(A.mat, vec);
-        f3 pl = mulTv(B.mat, pw - B.pos);
-        float px = B.size[0] - fabsf(pl.x), py = B.size[1] - fabsf(pl.y), pz = B.size[2] - fabsf(pl.z);
-        if (px >= -margin && py >= -margin && pz >= -margin) {
-          int k = 0; float best = px;
-          if (py < best) { best = py; k = 1; }
-          if (pz < best) { best = pz; k = 2; }
-          f3 nl = mk3(0, 0, 0);
-          float sg = comp(pl, k) >= 0 ? 1.f : -1.f;
-          if (k == 0) nl.x = sg; else if (k == 1) nl.y = sg; else nl.z = sg;
-          f3 nw = mulv(B.mat, nl);
-          hit = true; o.dist = -best; o.pos = pw + nw * (0.5f * best); o.n = pass == 0 ? nw * -1.f : nw;
-        }
-      }
+      hit = box_box_lane(c.lane, a, b, margin, o);
     }
     uint32_t bal = MJB_BALLOT(hit);
     int rank = MJB_POPC(bal & ((1u << c.lane) - 1u));
-    if (hit && rank < lim && ncon + rank < dm.maxcon) store_contact(c, ncon + rank, o, p, mu);
     int add = MJB_POPC(bal);
-    ncon += add < lim ? add : lim;
+    if (add > lim) add = lim;
+    const int copy = dm.pack > 1 ? g1 / dm.ngeom1 : 0;
+    int room = 0;
+#pragma unroll
+    for (int cp = 0; cp < MJB_MAX_PACK; cp++)
+      if (cp == copy) { room = dm.maxcon1 - tot[cp]; tot[cp] += add; }
+    if (room < 0) room = 0;
+    if (add > room) add = room;
+    if (hit && rank < add) store_contact(c, ncon + rank, o, p, mu);
+    ncon += add;
   }
-  if (ncon > dm.maxcon) ncon = dm.maxcon;
   MJB_SYNC();
   return ncon;
 }
@@ -1293,7 +1435,7 @@ MJB_DEV void sensors_acc(const Ctx& c, int ncon) {
 
 // =================================================================================================
 // one forward-dynamics evaluation: SF_qpos / qvel / ctrl -> SF_qacc.  Returns the contact count.
-MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out) {
+MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out, int* found) {
   fk(c);
   if (probes) {
     // exported positions belong to the LAST forward pass of the step (what `data.xipos` holds after
@@ -1311,7 +1453,12 @@ MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out) {
   crb_mass(c);
   rne_pass(c, false);
   MJB_CTA_SYNC(c.cta_threads);  // re-align the env-warps of the CTA before the data-dependent phases
-  int ncon = collide(c);
+  int tot[MJB_MAX_PACK] = {0, 0, 0, 0};
+  int ncon = collide(c, tot);
+  if (found) {   // contacts found beyond a copy's quota were dropped: keep the count visible (mjb_buffers.ncon_dropped)
+#pragma unroll
+    for (int cp = 0; cp < MJB_MAX_PACK; cp++) found[cp] += tot[cp] > c.dm->maxcon1 ? tot[cp] - c.dm->maxcon1 : 0;
+  }
   if (sensors) sensors_pos(c);
   if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
   make_constraints(c, ncon);
@@ -1348,7 +1495,7 @@ MJB_DEV void integrate_pos(const Ctx& c, float* qpos, const float* v, float h) {
 // is a single stage, RK4 four stages of the same loop (stages 2..4 without sensors).  SF_qacc keeps the
 // solver's qacc (not the damping-corrected one): it is the warm start of the next solve, as MuJoCo's
 // qacc_warmstart.
-MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) {
+MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out, int* dropped) {
   const DevModel& dm = *c.dm;
   const int nv = dm.nv, lane = c.lane;
   float *qpos = SF(qpos), *qvel = SF(qvel), *qacc = SF(qacc);
@@ -1373,7 +1520,7 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out) 
       if (lane < nv) qvel[lane] = v0[lane] + h * A * aprev;
       MJB_SYNC();
     }
-    ncon = forward(c, sensors && st == 0, sensors && st == nstage - 1, st == 0 ? iters_out : nullptr);
+    ncon = forward(c, sensors && st == 0, sensors && st == nstage - 1, st == 0 ? iters_out : nullptr, dropped);
     if (rk4) {
       const float Bw = (st == 0 || st == 3) ? (1.f / 6) : (1.f / 3);
       if (st == 0) {

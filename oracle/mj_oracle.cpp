@@ -256,7 +256,7 @@ int sphere_box(V3 c1, double r, V3 c2, const M3& R2, const double* size, double 
   out->frame[0] = n; out->frame[1] = V3();
   return 1;
 }
-// squared distance from a point (box frame) to the box
+// signed distance from a point (box frame) to the box: Euclidean outside, -(depth to the nearest face) inside
 double point_box_dist(V3 p, const double* size) {
   double s2 = 0, inside_pen = 1e300;
   for (int i = 0; i < 3; i++) {
@@ -266,35 +266,80 @@ double point_box_dist(V3 p, const double* size) {
   }
   return s2 > 0 ? std::sqrt(s2) : -inside_pen;
 }
+
+// capsule - box.  MuJoCo's mjc_CapsuleBox (engine_collision_box.c of the un-vendored mujoco==2.3.3) places
+// at most two spheres on the capsule axis and hands each to sphere - box: one at the point of the axis closest
+// to the box, and a second "clamped to the farthest point of the capsule that is above the box" when the
+// closest feature is a face.  Specification used here and by the CUDA kernel:
+//   1. t* = argmin over the segment of the signed distance to the box;
+//   2. if that point is inside the box: one contact there;
+//   3. else let k be the dominant axis of (point - closest box point), i.e. the closest FACE, and I the part of
+//      the segment whose projection lies inside that face's rectangle.  If t* lies in I (within 0.05 of the
+//      half length): contacts at the two ends of I, deeper first (the distance is linear over I, so the deeper
+//      end IS the closest point); ends closer than 1e-3 half lengths count once.  Otherwise (edge / vertex
+//      feature away from the face): one contact at t*.
+// Every sphere is margin-tested by sphere - box.  The minimiser is found EXACTLY here: the signed distance along
+// the segment is convex and piecewise quadratic / linear, with breakpoints where a coordinate crosses a face
+// plane or where two inside depths tie, so its minimum is at a breakpoint, an end, or the stationary point of
+// one quadratic piece.  (The kernel uses a golden-section search on the same function.)
 int capsule_box(V3 c1, const M3& R1, const double* size1, V3 c2, const M3& R2, const double* size2, double margin,
                 Contact* out) {
-  double r = size1[0], h = size1[1];
-  V3 ax = col(R1, 2);
-  V3 a = mulTv(R2, c1 - ax * h - c2), b = mulTv(R2, c1 + ax * h - c2);  // segment ends in the box frame
-  auto dist_at = [&](double t) { return point_box_dist(a + (b - a) * t, size2); };
-  // the distance from a point of a segment to a convex set is convex in t: golden-section search
-  double lo = 0, hi = 1;
-  const double gr = 0.6180339887498949;
-  double x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo), f1 = dist_at(x1), f2 = dist_at(x2);
-  for (int it = 0; it < 80; it++) {
-    if (f1 <= f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = dist_at(x1); }
-    else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = dist_at(x2); }
-  }
-  double tm = 0.5 * (lo + hi), dm = dist_at(tm), d0 = dist_at(0), d1 = dist_at(1);
-  int n = 0;
-  const double tie = 1e-6;
-  if (std::min(d0, d1) <= dm + tie) {
-    // an end point is (as good as) the deepest point: use the end spheres, deepest first
-    double ts[2] = {0, 1};
-    if (d1 < d0) { ts[0] = 1; ts[1] = 0; }
-    for (int k = 0; k < 2; k++) {
-      V3 cw = c1 + ax * ((2 * ts[k] - 1) * h);
-      n += sphere_box(cw, r, c2, R2, size2, margin, out + n);
+  const double r = size1[0], h = size1[1];
+  const V3 ax = col(R1, 2);
+  const V3 c = mulTv(R2, c1 - c2), d = mulTv(R2, ax) * h;   // p(t) = c + t d in the box frame, t in [-1, 1]
+  auto phi = [&](double t) { return point_box_dist(c + d * t, size2); };
+  std::vector<double> cand = {-1.0, 1.0};
+  auto add = [&](double t) { if (t > -1 && t < 1 && std::isfinite(t)) cand.push_back(t); };
+  // face-plane crossings: c_k + t d_k = +- s_k
+  for (int k = 0; k < 3; k++)
+    if (std::fabs(d[k]) > 1e-300) { add((size2[k] - c[k]) / d[k]); add((-size2[k] - c[k]) / d[k]); }
+  // ties of two inside depths: sa (c_a + t d_a) - s_a = sb (c_b + t d_b) - s_b
+  for (int a = 0; a < 3; a++)
+    for (int b = a + 1; b < 3; b++)
+      for (int sa = -1; sa <= 1; sa += 2)
+        for (int sb = -1; sb <= 1; sb += 2) {
+          double den = sa * d[a] - sb * d[b];
+          if (std::fabs(den) > 1e-300) add((sb * c[b] - size2[b] - sa * c[a] + size2[a]) / den);
+        }
+  // stationary points of the quadratic pieces: between consecutive breakpoints the set of violated coordinates and
+  // their signs are fixed, f^2 = sum_k (sg_k (c_k + t d_k) - s_k)^2 over that set
+  std::vector<double> brk = cand;
+  std::sort(brk.begin(), brk.end());
+  for (size_t i = 0; i + 1 < brk.size(); i++) {
+    double a = brk[i], b = brk[i + 1];
+    if (b - a < 1e-14) continue;
+    V3 pm = c + d * (0.5 * (a + b));
+    double num = 0, den = 0;
+    for (int k = 0; k < 3; k++) {
+      double sg = pm[k] > size2[k] ? 1.0 : (pm[k] < -size2[k] ? -1.0 : 0.0);
+      if (sg == 0) continue;
+      num += sg * d[k] * (sg * c[k] - size2[k]);
+      den += d[k] * d[k];
     }
-  } else {
-    V3 cw = c1 + ax * ((2 * tm - 1) * h);
-    n += sphere_box(cw, r, c2, R2, size2, margin, out + n);
+    if (den > 0) { double t = -num / den; if (t > a && t < b) cand.push_back(t); }
   }
+  std::sort(cand.begin(), cand.end());
+  double ts = cand[0], best = phi(cand[0]);
+  for (double t : cand) { double f = phi(t); if (f < best) { best = f; ts = t; } }
+  if (best > margin + r) return 0;
+  auto sphere_at = [&](double t, Contact* o) { return sphere_box(c1 + ax * (t * h), r, c2, R2, size2, margin, o); };
+  if (best <= 0) return sphere_at(ts, out);
+  // closest face and the part of the segment over its rectangle
+  V3 p = c + d * ts, sep;
+  for (int k = 0; k < 3; k++) sep[k] = p[k] - std::min(size2[k], std::max(-size2[k], p[k]));
+  int kf = 0;
+  for (int k = 1; k < 3; k++) if (std::fabs(sep[k]) > std::fabs(sep[kf])) kf = k;
+  double lo = -1, hi = 1;
+  for (int j = 0; j < 3; j++) {
+    if (j == kf) continue;
+    if (std::fabs(d[j]) < 1e-12) { if (std::fabs(c[j]) > size2[j]) { lo = 1; hi = -1; } continue; }
+    double t0 = (-size2[j] - c[j]) / d[j], t1 = (size2[j] - c[j]) / d[j];
+    lo = std::max(lo, std::min(t0, t1)); hi = std::min(hi, std::max(t0, t1));
+  }
+  if (lo > hi || ts < lo - 0.05 || ts > hi + 0.05) return sphere_at(ts, out);
+  double first = phi(lo) <= phi(hi) ? lo : hi, second = first == lo ? hi : lo;
+  int n = sphere_at(first, out);
+  if (hi - lo > 1e-3) n += sphere_at(second, out + n);
   return n;
 }
 int plane_box(V3 pp, V3 n, V3 c2, const M3& R2, const double* size, double margin, Contact* out) {
@@ -313,36 +358,100 @@ int plane_box(V3 pp, V3 n, V3 c2, const M3& R2, const double* size, double margi
   }
   return cnt;
 }
-// box-box: vertex/face contacts only (corners of one box inside the margin-inflated other box).
-// Edge-edge contacts are not generated — documented limitation; the reference's levels
-// never bring two boxes together under the benchmark protocols.
+// box - box by the separating-axis test + face clipping / edge - edge closest points (the construction behind
+// MuJoCo's mjc_BoxBox; un-vendored, restated from its documented behaviour: up to 8 contacts for face contact,
+// 1 for edge - edge, normal from geom1 to geom2, position midway between the surfaces).  Specification shared
+// with the CUDA kernel:
+//   * sep(L) = |L . (c2 - c1)| - r1(L) - r2(L) for the 6 face normals and the 9 unit edge cross products
+//     (pairs of edges with |cross| < 1e-6 are skipped); any sep > margin: no contact;
+//   * the contact axis is the face axis of largest sep (lowest index on ties) unless an edge axis beats it by
+//     more than 5 % of |sep| + 1e-6 (faces preferred, as in ODE-lineage implementations);
+//   * face axis: the incident face (most anti-parallel face of the other box) is clipped against the four side
+//     planes of the reference face; every vertex of the clipped polygon within `margin` of the reference plane
+//     is a contact with dist = its signed distance to that plane;
+//   * edge axis: one contact at the closest points of the two supporting edges, dist = sep.
+// Here the clipping is Sutherland - Hodgman on the polygon (sequential); the kernel enumerates the candidate
+// vertices of the same polygon in parallel.
 int box_box(V3 c1, const M3& R1, const double* s1, V3 c2, const M3& R2, const double* s2, double margin, Contact* out) {
-  int cnt = 0;
-  for (int pass = 0; pass < 2 && cnt < 8; pass++) {
-    V3 ca = pass == 0 ? c1 : c2, cb = pass == 0 ? c2 : c1;
-    const M3& Ra = pass == 0 ? R1 : R2; const M3& Rb = pass == 0 ? R2 : R1;
-    const double* sa = pass == 0 ? s1 : s2; const double* sb = pass == 0 ? s2 : s1;
-    for (int i = 0; i < 8 && cnt < 8; i++) {
-      V3 vec(sa[0] * ((i & 1) ? 1 : -1), sa[1] * ((i & 2) ? 1 : -1), sa[2] * ((i & 4) ? 1 : -1));
-      V3 pw = ca + mulv(Ra, vec);
-      V3 pl = mulTv(Rb, pw - cb);
-      int k = -1; double best = 1e300; bool in = true;
-      for (int a = 0; a < 3; a++) {
-        double pen = sb[a] - std::fabs(pl[a]);
-        if (pen < -margin) { in = false; break; }
-        if (pen < best) { best = pen; k = a; }
-      }
-      if (!in || best < -margin) continue;
-      // corner of A is within `margin` of (or inside) B; separate along B's nearest face
-      V3 nl; nl[k] = pl[k] >= 0 ? 1.0 : -1.0;     // outward normal of B's face (B frame)
-      V3 nw = mulv(Rb, nl);
-      // normal must point from geom1 to geom2
-      V3 n = pass == 0 ? nw * -1.0 : nw;
-      out[cnt].dist = -best;
-      out[cnt].pos = pw + nw * (best * 0.5);
-      out[cnt].frame[0] = n; out[cnt].frame[1] = V3();
-      cnt++;
+  const V3 dc = c2 - c1;
+  V3 A[3], B[3];
+  for (int i = 0; i < 3; i++) { A[i] = col(R1, i); B[i] = col(R2, i); }
+  auto radius = [&](V3 L, const V3* ax, const double* s) { return s[0] * std::fabs(dot(L, ax[0])) + s[1] * std::fabs(dot(L, ax[1])) + s[2] * std::fabs(dot(L, ax[2])); };
+  auto sep_of = [&](V3 L) { return std::fabs(dot(L, dc)) - radius(L, A, s1) - radius(L, B, s2); };
+  double fsep = -1e300, esep = -1e300;
+  int fax = -1, eax = -1;
+  for (int i = 0; i < 6; i++) {
+    double sp = sep_of(i < 3 ? A[i] : B[i - 3]);
+    if (sp > margin) return 0;
+    if (sp > fsep) { fsep = sp; fax = i; }
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      V3 L = cross(A[i], B[j]);
+      double len = norm(L);
+      if (len < 1e-6) continue;
+      double sp = sep_of(L * (1.0 / len));
+      if (sp > margin) return 0;
+      if (sp > esep) { esep = sp; eax = 3 * i + j; }
     }
+  if (eax >= 0 && esep > fsep + 0.05 * std::fabs(fsep) + 1e-6) {
+    const int i = eax / 3, j = eax % 3;
+    V3 L = normalized(cross(A[i], B[j]));
+    if (dot(L, dc) < 0) L = L * -1.0;
+    V3 pa = c1, pb = c2;   // points on the supporting edges: farthest along +L on box 1, along -L on box 2
+    for (int k = 0; k < 3; k++) {
+      if (k != i) pa = pa + A[k] * (s1[k] * (dot(L, A[k]) >= 0 ? 1.0 : -1.0));
+      if (k != j) pb = pb - B[k] * (s2[k] * (dot(L, B[k]) >= 0 ? 1.0 : -1.0));
+    }
+    // closest points of the lines pa + a A_i, pb + b B_j, parameters clamped to the edges
+    const V3 w = pa - pb;
+    const double ab = dot(A[i], B[j]), den = 1 - ab * ab;
+    double a = (ab * dot(B[j], w) - dot(A[i], w)) / den, b = (dot(B[j], w) - ab * dot(A[i], w)) / den;
+    a = std::min(s1[i], std::max(-s1[i], a)); b = std::min(s2[j], std::max(-s2[j], b));
+    const V3 qa = pa + A[i] * a, qb = pb + B[j] * b;
+    out[0].dist = esep; out[0].pos = (qa + qb) * 0.5; out[0].frame[0] = L; out[0].frame[1] = V3();
+    return 1;
+  }
+  // face contact: reference box owns the axis
+  const bool ref1 = fax < 3;
+  const int ri = ref1 ? fax : fax - 3;
+  const V3* RA = ref1 ? A : B; const V3* RB = ref1 ? B : A;
+  const double* sa = ref1 ? s1 : s2; const double* sb = ref1 ? s2 : s1;
+  const V3 ca = ref1 ? c1 : c2, cb = ref1 ? c2 : c1;
+  V3 nA = RA[ri];
+  if (dot(nA, cb - ca) < 0) nA = nA * -1.0;
+  int bj = 0;
+  for (int k = 1; k < 3; k++) if (std::fabs(dot(nA, RB[k])) > std::fabs(dot(nA, RB[bj]))) bj = k;
+  const V3 mB = RB[bj] * (dot(nA, RB[bj]) > 0 ? -1.0 : 1.0);   // outward normal of the incident face
+  const int bu = (bj + 1) % 3, bw = (bj + 2) % 3, au = (ri + 1) % 3, aw = (ri + 2) % 3;
+  std::vector<V3> poly;
+  const double sgn[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
+  for (int q = 0; q < 4; q++) poly.push_back(cb + mB * sb[bj] + RB[bu] * (sgn[q][0] * sb[bu]) + RB[bw] * (sgn[q][1] * sb[bw]));
+  for (int side = 0; side < 4; side++) {
+    const V3 e = RA[side < 2 ? au : aw] * (side % 2 ? -1.0 : 1.0);
+    const double lim = sa[side < 2 ? au : aw];
+    std::vector<V3> nxt;
+    for (size_t q = 0; q < poly.size(); q++) {
+      const V3 p0 = poly[q], p1 = poly[(q + 1) % poly.size()];
+      const double f0 = dot(p0 - ca, e) - lim, f1 = dot(p1 - ca, e) - lim;
+      if (f0 <= 0) nxt.push_back(p0);
+      if ((f0 < 0 && f1 > 0) || (f0 > 0 && f1 < 0)) nxt.push_back(p0 + (p1 - p0) * (f0 / (f0 - f1)));
+    }
+    poly.swap(nxt);
+    if (poly.empty()) break;
+  }
+  int cnt = 0;
+  for (size_t q = 0; q < poly.size() && cnt < 8; q++) {
+    bool dup = false;
+    for (size_t k = 0; k < q; k++) if (norm(poly[q] - poly[k]) < 1e-9) dup = true;
+    if (dup) continue;
+    const double dist = dot(poly[q] - ca, nA) - sa[ri];
+    if (dist > margin) continue;
+    out[cnt].dist = dist;
+    out[cnt].pos = poly[q] - nA * (0.5 * dist);
+    out[cnt].frame[0] = ref1 ? nA : nA * -1.0;
+    out[cnt].frame[1] = V3();
+    cnt++;
   }
   return cnt;
 }

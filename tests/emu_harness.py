@@ -54,7 +54,7 @@ class EmuBatch:
             "reward": np.zeros((N, max(1, A)), f), "term": np.zeros((N, A + 1), u), "trunc": np.zeros((N, A + 1), u),
             "timestep": np.zeros((N,), i), "store_i": np.zeros((N, max(1, A), lay.store_i32), i),
             "store_f": np.zeros((N, max(1, A), lay.store_f32), f), "ncon": np.zeros((N,), i),
-            "contact_geom": np.zeros((N, lay.maxcon, 2), i), "contact_dist": np.zeros((N, lay.maxcon), f), "niter": np.zeros((N,), i), "nreset": np.zeros((N,), i),
+            "contact_geom": np.zeros((N, lay.maxcon, 2), i), "contact_dist": np.zeros((N, lay.maxcon), f), "niter": np.zeros((N,), i), "nreset": np.zeros((N,), i), "ncon_dropped": np.zeros((N,), i),
         }
         self.B = L.Buffers()
         for k, v in self.buf.items():
