@@ -159,7 +159,9 @@ typedef struct mjb_buffers {
 /* data_store column ids */
 enum { MJB_STORE_I_UTTERANCE = 0, MJB_STORE_I_HAS_UTTERANCE = 1, MJB_STORE_I_TARGET = 2, MJB_STORE_I_INVENTORY = 3,
        MJB_STORE_I_HAS_XPOS = 4, MJB_STORE_I_DRAWS = 5, MJB_STORE_I_COUNT = 8 };
-enum { MJB_STORE_F_DISTANCE = 0, MJB_STORE_F_XPOS_BEFORE = 1, MJB_STORE_F_COUNT = 4 };
+/* DISTANCE64: the same distance as an fp64 value spread over two float columns (the reward / done arithmetic runs
+ * in fp64 like the reference's math.dist on float64 views, mujoco_parent.py:449) */
+enum { MJB_STORE_F_DISTANCE = 0, MJB_STORE_F_XPOS_BEFORE = 1, MJB_STORE_F_DISTANCE64 = 2, MJB_STORE_F_COUNT = 4 };
 
 /* ---- batch (CUDA) ---------------------------------------------------------------------------- */
 int mjb_batch_layout(const mjb_model* m, const mjb_env_spec* spec, int32_t num_envs, mjb_layout* out);
@@ -178,7 +180,11 @@ int mjb_physics(mjb_batch* b, int32_t skip_frames);
 /* forward pass only (mj_forward): kinematics, collisions, sensors; no integration */
 int mjb_forward(mjb_batch* b);
 int mjb_sync(mjb_batch* b);
-/* host-buffer call: H2D actions, step, D2H obs/reward/flags, synchronises.  Layouts as above. */
+/* host-buffer call: H2D actions, step, D2H obs/reward/flags, synchronises.  Layouts as above.
+ * When all five arrays are page-locked (cudaHostAlloc / torch pin_memory) the kernel writes obs / reward / term /
+ * trunc straight into them (zero-copy) and the DEVICE copies buffers.obs / reward / term / trunc are NOT updated by
+ * that call: read the results from the host arrays.  State buffers (qpos, qvel, store, timestep ...) are always
+ * updated.  MJB_HOST_ZEROCOPY=0 restores "device buffers written, then copied". */
 int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward, uint8_t* term, uint8_t* trunc);
 /* number of kernel launches issued so far by this handle */
 int64_t mjb_launch_count(const mjb_batch* b);
@@ -195,7 +201,7 @@ int mjb_set_env_order(mjb_batch* b, const int32_t* order_dev);
  * assigned to its level.  `env_ids_dev` lists `count` distinct env indices in [0, num_envs) (device memory,
  * must stay valid until replaced); NULL restores "all envs".  Needs a batch created with MJB_SPEC_NO_PACK.
  * A reset mask stays indexed by env id. */
-int mjb_set_env_subset(mjb_batch* b, const int32_t* env_ids_dev, int32_t count);
+int mjb_set_env_subset(mjb_batch* b, const int32_t* env_ids_dev, int32_t count);   /* (non-NULL, 0) = no env at all */
 /* Agent cameras (`get_camera_data`, mujoco_parent.py:518-556): renders `ncams` fixed cameras (model camera ids,
  * host array; mjb_name2id with MJB_OBJ_CAMERA) of every env from its current qpos into
  * rgb_dev = u8 [num_envs, ncams, height, width, 3] (device), rows bottom-up as glReadPixels returns them.

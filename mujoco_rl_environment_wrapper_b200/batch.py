@@ -137,6 +137,9 @@ class Batch:
 
     # ---- host-buffer step: numpy in / numpy out, copies inside
     def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, term: np.ndarray, trunc: np.ndarray):
+        """One step through host arrays.  With page-locked arrays (host_arrays()) the kernel writes the results into
+        them directly and the device tensors self.obs / reward / term / trunc keep their previous contents
+        (include/mjb.h, mjb_step_host); the state tensors are always current."""
         L.check(self._lib.mjb_step_host(self._h, actions.ctypes.data, obs.ctypes.data, reward.ctypes.data,
                                         term.ctypes.data, trunc.ctypes.data), "step_host")
 

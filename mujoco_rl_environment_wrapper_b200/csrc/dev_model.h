@@ -133,6 +133,7 @@ struct DevModel {
   int pack, a1, t1, nq1, nv1, nu1, ns1, np1, ngeom1, maxcon1;
   int integrator, has_damping, need_acc_sensors;
   float timestep, gravity[3];
+  double timestep_d;   // opt.timestep as compiled (fp64): the ant reward divides by it like the reference
   int solver_iterations, ls_iterations;
   float solver_tol;
   float reset_noise;   // 0: resets start exactly at qpos0 (reference behaviour)

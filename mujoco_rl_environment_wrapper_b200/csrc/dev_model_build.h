@@ -87,7 +87,7 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
 
   dm.nq = m.nq; dm.nv = m.nv; dm.nu = m.nu; dm.nmb = nmb; dm.njnt = m.njnt; dm.ngeom = m.ngeom;
   dm.nsite = m.nsite; dm.nsensor = m.nsensor; dm.nsensordata = m.nsensordata; dm.npair = m.npair;
-  dm.nlevel = nlevel; dm.integrator = m.integrator; dm.timestep = (float)m.timestep;
+  dm.nlevel = nlevel; dm.integrator = m.integrator; dm.timestep = (float)m.timestep; dm.timestep_d = m.timestep;
   for (int i = 0; i < 3; i++) dm.gravity[i] = (float)m.gravity[i];
   dm.ldj = m.nv | 1;  // narrowed below to the widest contact dof mask
   dm.solver_iterations = spec.solver_iterations > 0 ? spec.solver_iterations : env_int("MJB_SOLVER_ITERS", 24);

@@ -18,23 +18,36 @@ MJB_HD uint32_t draw_u32(unsigned long long seed, uint32_t env, uint32_t agent, 
   return (uint32_t)(z >> 32);
 }
 
-MJB_DEV float probe_dist(const float* probe, int a, int b) {
-  float dx = probe[4 * a] - probe[4 * b], dy = probe[4 * a + 1] - probe[4 * b + 1], dz = probe[4 * a + 2] - probe[4 * b + 2];
-  return sqrtf(dx * dx + dy * dy + dz * dz);
+// Distances, the reward arithmetic and the done comparison run in fp64 on the fp32 positions (the reference computes
+// math.dist on float64 numpy views, mujoco_parent.py:428-449): given identical xipos the reward, cast to fp32, and the
+// done flag are those of the reference's own arithmetic.  The stored distance keeps its fp64 value in two store_f
+// columns (MJB_STORE_F_DISTANCE64, +1) next to the fp32 copy that `data_store[agent]["distance"]` shows.
+MJB_DEV double probe_dist(const float* probe, int a, int b) {
+  const double dx = (double)probe[4 * a] - (double)probe[4 * b], dy = (double)probe[4 * a + 1] - (double)probe[4 * b + 1],
+               dz = (double)probe[4 * a + 2] - (double)probe[4 * b + 2];
+  return sqrt(dx * dx + dy * dy + dz * dz);
+}
+MJB_DEV double ld_dist(const float* sfa) {
+  union { double d; float f[2]; } u;
+  u.f[0] = sfa[MJB_STORE_F_DISTANCE64]; u.f[1] = sfa[MJB_STORE_F_DISTANCE64 + 1];
+  return u.d;
+}
+MJB_DEV void st_dist(float* sfa, double d) {
+  union { double d; float f[2]; } u;
+  u.d = d;
+  sfa[MJB_STORE_F_DISTANCE64] = u.f[0]; sfa[MJB_STORE_F_DISTANCE64 + 1] = u.f[1];
+  sfa[MJB_STORE_F_DISTANCE] = (float)d;
 }
 
 // the dynamics / reward / done programme of one env, executed by one lane in the reference's order
 // (dynamic outer, agent inner; then reward fn outer, agent inner; truncation; done fns with early exit)
-MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, int copy, bool is_reset, const float* probe, int* si,
-                         float* sf, const float* act, int* ts_io) {
+// `obs` / `rew` / `term` / `trunc` are the env's own result rows ([A, obs_stride], [A], [A + 1], [A + 1]; global or
+// shared memory), `ctrl` the env's ctrl row (read by the ant reward), `probe` its exported positions.
+MJB_DEV void run_plugins(const DevModel& dm, const float* ctrl, float* obs, float* rew, uint8_t* term, uint8_t* trunc, int env, int copy,
+                         bool is_reset, const float* probe, int* si, float* sf, const float* act, int* ts_io) {
   // `env` is the REAL environment, `copy` its slot inside the (possibly packed) virtual env of this warp
-  const DevModel& dm = *c.dm;
   const int A = dm.a1, ab = copy * dm.a1, tb = copy * dm.t1, n_targets = dm.t1;
-  float* obs = B.obs + (size_t)env * A * dm.obs_stride;
-  float* rew = B.reward + (size_t)env * A;
-  uint8_t* term = B.term + (size_t)env * (A + 1);
-  uint8_t* trunc = B.trunc + (size_t)env * (A + 1);
-  float reward[MJB_MAX_AGENTS];
+  double reward[MJB_MAX_AGENTS];
   bool done[MJB_MAX_AGENTS];
   int opos[MJB_MAX_AGENTS];
   if (is_reset)  // data_store = {agent: {}} (mujoco_rl.py:312); the draw counter is not part of the store
@@ -46,7 +59,7 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, int copy, 
       for (int k = 0; k < dm.store_f32; k++) sf[a * dm.store_f32 + k] = 0.f;
     }
   MJB_NOUNROLL
-  for (int a = 0; a < A; a++) { reward[a] = 0.f; done[a] = false; opos[a] = dm.obs_adr[ab + a + 1] - dm.obs_adr[ab + a]; }
+  for (int a = 0; a < A; a++) { reward[a] = 0.0; done[a] = false; opos[a] = dm.obs_adr[ab + a + 1] - dm.obs_adr[ab + a]; }
   MJB_NOUNROLL
   for (int p = 0; p < dm.n_dynamics; p++) {
     const DevPlugin& dyn = dm.dynamics[p];
@@ -69,13 +82,13 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, int copy, 
           sia[MJB_STORE_I_TARGET] = tgt;
         }
         if (tgt > 0) {
-          float d = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
-          if (d < dyn.param[0]) {
+          const double d = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
+          if (d < (double)dyn.param[0]) {
             sia[MJB_STORE_I_INVENTORY] ^= 1;
-            reward[a] += 1.f;
+            reward[a] += 1.0;
             tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)n_targets);
             sia[MJB_STORE_I_TARGET] = tgt;
-            sfa[MJB_STORE_F_DISTANCE] = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
+            st_dist(sfa, probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]));
           }
           const float* tp = probe + 4 * dm.target_probe[tb + tgt - 1];
           oa[opos[a]] = tp[0]; oa[opos[a] + 1] = tp[1]; oa[opos[a] + 2] = tp[2];
@@ -114,22 +127,23 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, int copy, 
         if (tgt == 0) {
           tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)n_targets);
           sia[MJB_STORE_I_TARGET] = tgt;
-          sfa[MJB_STORE_F_DISTANCE] = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
+          st_dist(sfa, probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]));
         } else {
-          float d = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
-          reward[a] += (sfa[MJB_STORE_F_DISTANCE] - d) * rf.param[0];
-          sfa[MJB_STORE_F_DISTANCE] = d;
+          const double d = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
+          reward[a] += (ld_dist(sfa) - d) * (double)rf.param[0];
+          st_dist(sfa, d);
         }
       } else if (rf.kind == MJB_REW_ANT) {
         float x_after = probe[4 * dm.agent_probe[ab + a]];
         if (!sia[MJB_STORE_I_HAS_XPOS]) {
           sia[MJB_STORE_I_HAS_XPOS] = 1;
         } else {
-          float cc = 0.f;
+          double cc = 0.0;
           MJB_NOUNROLL
-          for (int u = 0; u < dm.nu1; u++) cc += SF(ctrl)[copy * dm.nu1 + u] * SF(ctrl)[copy * dm.nu1 + u];
-          // contact cost term: cfrc_ext is zero on these models (no force/acc sensors), SURVEY Q11
-          reward[a] += (x_after - sfa[MJB_STORE_F_XPOS_BEFORE]) / dm.timestep - 0.5f * cc;
+          for (int u = 0; u < dm.nu1; u++) cc += (double)ctrl[u] * (double)ctrl[u];
+          // contact cost term: cfrc_ext is zero on these models (no force / acc sensors); the Python
+          // layer refuses to fuse this reward for models with accelerometers, where MuJoCo fills cfrc_ext
+          reward[a] += ((double)x_after - (double)sfa[MJB_STORE_F_XPOS_BEFORE]) / dm.timestep_d - 0.5 * cc;
         }
         sfa[MJB_STORE_F_XPOS_BEFORE] = x_after;
       }
@@ -145,12 +159,12 @@ MJB_DEV void run_plugins(const Ctx& c, const mjb_buffers& B, int env, int copy, 
     const DevPlugin& df = dm.dones[p];
     MJB_NOUNROLL
     for (int a = 0; a < A; a++)
-      if (df.kind == MJB_DONE_DISTANCE_LE) done[a] = done[a] || (sf[a * dm.store_f32 + MJB_STORE_F_DISTANCE] <= df.param[0]);
+      if (df.kind == MJB_DONE_DISTANCE_LE) done[a] = done[a] || (ld_dist(sf + a * dm.store_f32) <= (double)df.param[0]);
     MJB_NOUNROLL
     for (int a = 0; a < A; a++) all = all || done[a];
   }
   MJB_NOUNROLL
-  for (int a = 0; a < A; a++) { rew[a] = reward[a]; term[a] = done[a] ? 1 : 0; }
+  for (int a = 0; a < A; a++) { rew[a] = (float)reward[a]; term[a] = done[a] ? 1 : 0; }
   term[A] = all ? 1 : 0;
   *ts_io = ts + 1;
 }
@@ -303,8 +317,8 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
   const int passes = integrate ? skip_frames : 1;
   int niter = 0;
   if (PHYS) {
-    MJB_NOUNROLL
     int dropped[MJB_MAX_PACK] = {0, 0, 0, 0};
+    MJB_NOUNROLL
     for (int f = 0; f < passes; f++) ncon = substep(c, f == passes - 1, integrate, &niter, dropped);
     if (B.ncon_dropped && lane == 0) {   // cumulative per real env: stays 0 while no contact was ever dropped
 #pragma unroll
@@ -452,7 +466,9 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
       if (lane == 0) *s_ts = B.timestep[env];
     }
     MJB_SYNC();
-    if (lane == 0) run_plugins(c, B, env, k, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
+    if (lane == 0)
+      run_plugins(dm, SF(ctrl) + k * dm.nu1, B.obs + (size_t)env * A1 * dm.obs_stride, B.reward + (size_t)env * A1, B.term + (size_t)env * (A1 + 1),
+                  B.trunc + (size_t)env * (A1 + 1), env, k, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
     MJB_SYNC();
     for (int i = lane; i < A1 * dm.store_i32; i += 32) gsi[i] = s_si[i];
     if (lane < A1 * dm.store_f32) gsf[lane] = s_sf[lane];

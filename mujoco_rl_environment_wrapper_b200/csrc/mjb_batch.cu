@@ -11,6 +11,8 @@
 #include "dev_model_build.h"
 #include "env_kernel.cuh"
 #include "render_kernel.cuh"
+#include "tma_prims.cuh"
+#include "lite_kernel.cuh"
 #include "mjb_internal.h"
 
 #ifndef MJB_MAX_THREADS
@@ -18,33 +20,6 @@
 #endif
 
 namespace mjb {
-
-// ---- TMA bulk copy of the constant image into shared memory (SASS: UBLKCP + SYNCS) ---------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 
 // One CTA per SM, `warps` environments in flight per CTA; each warp walks the env index space with a grid-wide
 // stride (envs are independent: the warps only meet at the staging of the model image and at the round barrier).
@@ -61,7 +36,7 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -118,6 +93,9 @@ struct mjb_batch {
   bool has_lite = false;
   int lite_warps = 0, lite_grid = 0;
   size_t lite_smem = 0;
+  mjb::LiteLayout tile{};   // skipFrames = 0: tile kernel geometry
+  int tile_grid = 0;
+  size_t tile_smem = 0;
   mjb_buffers B;
   int num_envs = 0, device = 0, warps = 0, grid = 0;
   size_t smem_bytes = 0;
@@ -173,8 +151,12 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStr
   b->next_slot = (b->next_slot + 1) % 64;
   if (b->lockstep == 0)  // only the dynamic scheduler consumes the counter
     CUDA_TRY(cudaMemcpyAsync(counter, &b->h_first[0], sizeof(int), cudaMemcpyHostToDevice, stream));
-  if (mode == mjb::MODE_STEP && b->has_lite) {
-    // no physics in the step: many small envs per SM, rounds aligned the same way
+  if (mode == mjb::MODE_STEP && b->has_lite && !b->subset) {
+    // no physics in the step: the bandwidth-shaped tile kernel (lite_kernel.cuh) over the contiguous env range
+    const int ntiles = (active + b->tile.tile - 1) / b->tile.tile;
+    mjb::k_lite<<<std::min(ntiles, b->tile_grid), LITE_THREADS, b->tile_smem, stream>>>(b->lite.dm, b->d_image, B, b->tile, active, base);
+  } else if (mode == mjb::MODE_STEP && b->has_lite) {
+    // an env-id list (level variants) is not a contiguous range: the warp-per-env form of the same step
     mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, stream>>>(b->lite.dm, b->d_image, B, b->num_envs, mode,
                                                                                    skip_frames, mask, counter, 2, b->subset, active, base);
   } else {
@@ -292,6 +274,22 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     }
     b->lite_grid = std::min((num_envs + b->lite_warps - 1) / b->lite_warps, prop.multiProcessorCount * per_sm);
     b->has_lite = true;
+    // tile kernel: the largest tile of 64 / 32 / 16 envs whose rows fit 48 KB, so that several CTAs share an SM and
+    // keep enough bytes in flight for HBM
+    int tile = std::max(16, mjb::env_int("MJB_LITE_TILE", 64) / 16 * 16);
+    for (;;) {
+      b->tile = mjb::make_lite_layout(b->lite.dm, tile);
+      b->tile_smem = 16 + (size_t)b->tile.words * 4;
+      if (b->tile_smem <= 48 * 1024 || tile <= 16) break;
+      tile /= 2;
+    }
+    int tile_per_sm = 1;
+    if (b->tile_smem > max_smem || cudaFuncSetAttribute(mjb::k_lite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->tile_smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tile_per_sm, mjb::k_lite, LITE_THREADS, b->tile_smem) != cudaSuccess || tile_per_sm < 1) {
+      mjb::set_error("tile step kernel configuration failed (rows of one env too large for shared memory)");
+      return fail(MJB_ERR_CUDA);
+    }
+    b->tile_grid = prop.multiProcessorCount * tile_per_sm;
   }
   if (cudaMalloc(&b->d_image, (size_t)dm.image_words * 4) != cudaSuccess ||
       cudaMemcpy(b->d_image, b->img.words.data(), (size_t)dm.image_words * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -428,7 +426,21 @@ int mjb_step_host(mjb_batch* b, const float* actions, float* obs, float* reward,
       CUDA_TRY(cudaStreamSynchronize(b->stream));
       return MJB_OK;
     }
-    cudaGetLastError();   // not device-addressable after all: fall through to the copying paths
+    // not device-addressable after all (e.g. an address remembered as page-locked was freed and re-used by pageable
+    // memory): forget what was remembered and take the staged path for this call
+    cudaGetLastError();
+    for (auto& p : b->pin_cache) p = nullptr;
+    memcpy(b->h_act, actions, nb_act);
+    CUDA_TRY(cudaMemcpyAsync(b->B.actions, b->h_act, nb_act, cudaMemcpyHostToDevice, b->stream));
+    int rc = launch(b, mjb::MODE_STEP, dm.skip_frames, nullptr);
+    if (rc != MJB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(b->h_obs, b->B.obs, nb_obs, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->h_rew, b->B.reward, nb_rew, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->h_term, b->B.term, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->h_trunc, b->B.trunc, nb_flag, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    memcpy(obs, b->h_obs, nb_obs); memcpy(reward, b->h_rew, nb_rew); memcpy(term, b->h_term, nb_flag); memcpy(trunc, b->h_trunc, nb_flag);
+    return MJB_OK;
   }
   // Two halves on two streams: the second half's actions go up while the first half computes, and the first
   // half's observations come down while the second half computes.

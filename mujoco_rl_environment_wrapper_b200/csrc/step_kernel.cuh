@@ -1174,12 +1174,12 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     if (done) continue;
     it++;
     // Hessian H = M + J' diag(D active) J (packed lower triangle)
-    MJB_NOUNROLL
     {
       // both triangles start 16 B aligned and are padded to a multiple of 4 words: copy as 128-bit words
       struct alignas(16) W4 { float a, b, c, d; };
       const W4* src = (const W4*)M;
       W4* dst = (W4*)H;
+      MJB_NOUNROLL
       for (int i = lane; i < ((nv * (nv + 1)) / 2 + 3) / 4; i += 32) dst[i] = src[i];
     }
     MJB_SYNC();

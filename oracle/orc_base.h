@@ -214,27 +214,32 @@ inline void point_jacobian(const Model& m, const Kin& k, int body, V3 point, std
   }
 }
 
-// M = sum over bodies of  m Jp' Jp + Jr' (R I R') Jr  at the centre of mass, + armature; dense nv x nv
+// M = sum over bodies of  m Jp' Jp + Jr' (R I R') Jr  at the centre of mass, + armature; dense nv x nv.  A body's
+// Jacobian columns are non-zero only for the dofs between it and the world, so the products run over that list.
 inline void mass_matrix(const Model& m, const Kin& k, std::vector<double>& M) {
   const int nv = m.nv;
   M.assign((size_t)nv * nv, 0.0);
-  std::vector<double> jp, jr, IJ(3 * nv);
+  std::vector<double> jp, jr;
+  std::vector<int> dofs;
   for (int b = 1; b < m.nbody; b++) {
     if (m.body_mass[b] <= 0) continue;
+    dofs.clear();
+    for (int a = b; a > 0; a = m.body_parentid[a])
+      for (int d = m.body_dofadr[a]; d >= 0 && d < m.body_dofadr[a] + m.body_dofnum[a]; d++) dofs.push_back(d);
+    if (dofs.empty()) continue;
     point_jacobian(m, k, b, k.xipos[b], jp, jr);
     const M3& R = k.ximat[b];
     double Iw[9];
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++)
         Iw[3 * r + c] = R(r, 0) * m.body_inertia[3 * b] * R(c, 0) + R(r, 1) * m.body_inertia[3 * b + 1] * R(c, 1) + R(r, 2) * m.body_inertia[3 * b + 2] * R(c, 2);
-    for (int r = 0; r < 3; r++)
-      for (int d = 0; d < nv; d++) IJ[r * nv + d] = Iw[3 * r] * jr[d] + Iw[3 * r + 1] * jr[nv + d] + Iw[3 * r + 2] * jr[2 * nv + d];
-    for (int i = 0; i < nv; i++)
-      for (int j = 0; j < nv; j++) {
-        double s = 0;
-        for (int r = 0; r < 3; r++) s += m.body_mass[b] * jp[r * nv + i] * jp[r * nv + j] + jr[r * nv + i] * IJ[r * nv + j];
-        M[(size_t)i * nv + j] += s;
-      }
+    for (int i : dofs) {
+      const double wi[3] = {jr[i], jr[nv + i], jr[2 * nv + i]};
+      const double Iwi[3] = {Iw[0] * wi[0] + Iw[1] * wi[1] + Iw[2] * wi[2], Iw[3] * wi[0] + Iw[4] * wi[1] + Iw[5] * wi[2], Iw[6] * wi[0] + Iw[7] * wi[1] + Iw[8] * wi[2]};
+      for (int j : dofs)
+        M[(size_t)i * nv + j] += m.body_mass[b] * (jp[i] * jp[j] + jp[nv + i] * jp[nv + j] + jp[2 * nv + i] * jp[2 * nv + j]) +
+                                 Iwi[0] * jr[j] + Iwi[1] * jr[nv + j] + Iwi[2] * jr[2 * nv + j];
+    }
   }
   for (int d = 0; d < nv; d++) M[(size_t)d * nv + d] += m.dof_armature[d];
 }
