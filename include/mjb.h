@@ -77,6 +77,7 @@ enum { MJB_DONE_DISTANCE_LE = 1 /* README.md:168-173: data_store[agent]["distanc
 #define MJB_MAX_AGENTS 8
 #define MJB_MAX_PLUGINS 4
 #define MJB_MAX_TARGETS 16
+#define MJB_MAX_EXTRA_PROBES 48
 
 typedef struct mjb_plugin {
   int32_t kind;      /* MJB_DYN_* / MJB_REW_* / MJB_DONE_* */
@@ -114,6 +115,12 @@ typedef struct mjb_env_spec {
   float reset_noise;                  /* 0 = every reset starts at qpos0 / zero velocity like the reference
                                          (mujoco_parent.py:349); > 0: hinge / slide qpos and all qvel start at
                                          +- reset_noise (uniform, counter-based stream) to decorrelate envs */
+  /* extra exported positions beyond the agents and the targets (`distance` / `get_data` / `data.body(n).xipos` for
+   * other objects, mujoco_parent.py:394-449): MJB_OBJ_BODY (xipos) or MJB_OBJ_GEOM (xpos) ids.  A spec with extra
+   * probes is never packed (one env per warp). */
+  int32_t n_extra_probes;
+  int32_t extra_objtype[MJB_MAX_EXTRA_PROBES];
+  int32_t extra_objid[MJB_MAX_EXTRA_PROBES];
 } mjb_env_spec;
 
 /* mjb_env_spec.flags */
@@ -126,7 +133,7 @@ typedef struct mjb_layout {
   int32_t qpos_stride, qvel_stride, ctrl_stride, sensor_stride; /* floats per env row (16 B aligned) */
   int32_t act_stride;   /* floats per (env, agent) */
   int32_t obs_stride;   /* floats per (env, agent) */
-  int32_t probe_count;  /* exported positions: agents' bodies then targets */
+  int32_t probe_count;  /* exported positions: agents' bodies, then targets, then extra probes */
   int32_t maxcon;       /* contact slots per env */
   int32_t store_i32, store_f32; /* per (env, agent) data_store columns */
 } mjb_layout;
@@ -152,6 +159,9 @@ typedef struct mjb_buffers {
   int32_t* niter;        /* [N] or NULL: Newton iterations of the last forward pass (diagnostic) */
   int32_t* nreset;       /* [N] or NULL: how often the env was auto-reset because its state became non-finite
                             (MuJoCo's mj_checkPos / mj_checkVel behaviour: warn and mj_resetData) */
+  float* probe_quat;     /* [N, probe_count, 4] or NULL: orientation (w, x, y, z) of every exported MOVING body (xmat) /
+                            geom (geom xmat) from the same forward pass as `probe`; rows of static objects are left to
+                            the caller (constants).  Feeds get_data()["orientation"], mujoco_parent.py:407,419 */
   int32_t* ncon_dropped; /* [N] or NULL: cumulative count of contacts found beyond the env's `maxcon` slots and
                             therefore dropped (MuJoCo grows its arena instead); 0 = every contact was simulated */
 } mjb_buffers;

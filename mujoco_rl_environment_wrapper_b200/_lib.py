@@ -9,7 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmjb.so")
 
-MAX_AGENTS, MAX_PLUGINS, MAX_TARGETS = 8, 4, 16
+MAX_AGENTS, MAX_PLUGINS, MAX_TARGETS, MAX_EXTRA_PROBES = 8, 4, 16, 48
 SPEC_NO_PACK = 1   # mjb_env_spec.flags
 OBJ_BODY, OBJ_JOINT, OBJ_GEOM, OBJ_SITE, OBJ_CAMERA, OBJ_ACTUATOR, OBJ_SENSOR = 1, 3, 5, 6, 7, 19, 20
 DYN_LANGUAGE, DYN_PICKUP = 1, 2
@@ -46,6 +46,7 @@ class EnvSpec(ctypes.Structure):
         ("target_objtype", ctypes.c_int32 * MAX_TARGETS), ("target_objid", ctypes.c_int32 * MAX_TARGETS),
         ("seed", ctypes.c_uint64),
         ("solver_iterations", ctypes.c_int32), ("ls_iterations", ctypes.c_int32), ("flags", ctypes.c_int32), ("reset_noise", ctypes.c_float),
+        ("n_extra_probes", ctypes.c_int32), ("extra_objtype", ctypes.c_int32 * MAX_EXTRA_PROBES), ("extra_objid", ctypes.c_int32 * MAX_EXTRA_PROBES),
     ]
 
 
@@ -58,7 +59,7 @@ class Layout(ctypes.Structure):
 class Buffers(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("qpos", "qvel", "ctrl", "warmstart", "sensordata", "probe", "actions", "obs", "reward", "term",
-                 "trunc", "timestep", "store_i", "store_f", "ncon", "contact_geom", "contact_dist", "niter", "nreset", "ncon_dropped")]
+                 "trunc", "timestep", "store_i", "store_f", "ncon", "contact_geom", "contact_dist", "niter", "nreset", "probe_quat", "ncon_dropped")]
 
 
 _LIB = None

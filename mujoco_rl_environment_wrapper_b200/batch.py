@@ -14,7 +14,7 @@ from . import _lib as L
 
 
 class Batch:
-    def __init__(self, model: "L.Model", spec: "L.EnvSpec", num_envs: int, device=None, keepalive=(), share=None):
+    def __init__(self, model: "L.Model", spec: "L.EnvSpec", num_envs: int, device=None, keepalive=(), share=None, probe_quat=False):
         """`share`: another Batch whose tensors this handle steps as well (level variants, see set_subset);
         the two models must produce the same buffer layout."""
         self._lib = L.load()
@@ -53,6 +53,10 @@ class Batch:
             "store_f": z((N, max(1, A), lay.store_f32), f32), "ncon": z((N,), i32),
             "contact_geom": z((N, lay.maxcon, 2), i32), "contact_dist": z((N, lay.maxcon), f32), "niter": z((N,), i32), "nreset": z((N,), i32), "ncon_dropped": z((N,), i32),
         }
+        if share is None and probe_quat and lay.probe_count > 0:
+            q = z((N, lay.probe_count, 4), f32)
+            q[:, :, 0] = 1.0
+            self.buf["probe_quat"] = q
         B = L.Buffers()
         for k, v in self.buf.items():
             setattr(B, k, v.data_ptr())

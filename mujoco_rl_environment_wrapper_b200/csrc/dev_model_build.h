@@ -445,6 +445,9 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   }
   for (int a = 0; a <= spec.n_agents; a++) dm.obs_adr[a] = spec.obs_adr[a];
   for (int t = 0; t < spec.n_targets; t++) dm.target_probe[t] = add_probe(spec.target_objtype[t], spec.target_objid[t]);
+  if (spec.n_extra_probes < 0 || spec.n_extra_probes > MJB_MAX_EXTRA_PROBES) throw std::runtime_error("too many extra probes");
+  if (spec.n_extra_probes > 0 && pack > 1) throw std::runtime_error("extra probes need an unpacked batch");
+  for (int x = 0; x < spec.n_extra_probes; x++) add_probe(spec.extra_objtype[x], spec.extra_objid[x]);
   dm.nprobe = (int)pk.size();
   w.begin(IF_probe_kind); for (int v : pk) w.i(v); if (pk.empty()) w.i(0);
   w.begin(IF_probe_id); for (int v : pid) w.i(v); if (pid.empty()) w.i(0);
@@ -590,7 +593,7 @@ inline int choose_pack(const HostModel& host, const mjb_env_spec& spec, int num_
   K = std::min(K, std::min(4, env_int("MJB_PACK", 4)));   // 4 = MJB_MAX_PACK (per-copy contact quotas in step_kernel.cuh)
   K = std::min(K, num_envs);
   if (spec.skip_frames == 0) K = 1;   // no physics in the step: nothing to share
-  if (spec.flags & MJB_SPEC_NO_PACK) K = 1;
+  if ((spec.flags & MJB_SPEC_NO_PACK) || spec.n_extra_probes > 0) K = 1;
   return std::max(1, K);
 }
 

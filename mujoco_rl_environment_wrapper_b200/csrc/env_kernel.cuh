@@ -8,6 +8,13 @@ namespace mjb {
 
 enum { MODE_STEP = 0, MODE_PHYSICS = 1, MODE_FORWARD = 2, MODE_RESET = 3 };
 
+// agent loops of run_plugins: unrolled when the bound is small (registers), rolled in the general form (code size)
+#if defined(MJB_HOST_EMU)
+#define MJB_AGENT_LOOP
+#else
+#define MJB_AGENT_LOOP _Pragma("unroll (AMAX <= 2 ? 2 : 1)")
+#endif
+
 // counter-based draw replacing `random.randint` (README.md:154, Testing/Pick_Up_Dynamic.py:28,38)
 MJB_HD uint32_t draw_u32(unsigned long long seed, uint32_t env, uint32_t agent, uint32_t counter) {
   unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (1ull + env) + 0xBF58476D1CE4E5B9ull * agent +
@@ -43,28 +50,31 @@ MJB_DEV void st_dist(float* sfa, double d) {
 // (dynamic outer, agent inner; then reward fn outer, agent inner; truncation; done fns with early exit)
 // `obs` / `rew` / `term` / `trunc` are the env's own result rows ([A, obs_stride], [A], [A + 1], [A + 1]; global or
 // shared memory), `ctrl` the env's ctrl row (read by the ant reward), `probe` its exported positions.
+// AMAX bounds the agent loops at compile time: with a small AMAX (the tile kernel uses 2) the per-agent accumulators
+// live in registers and the loops unroll; MJB_MAX_AGENTS is the general form.
+template <int AMAX>
 MJB_DEV void run_plugins(const DevModel& dm, const float* ctrl, float* obs, float* rew, uint8_t* term, uint8_t* trunc, int env, int copy,
                          bool is_reset, const float* probe, int* si, float* sf, const float* act, int* ts_io) {
   // `env` is the REAL environment, `copy` its slot inside the (possibly packed) virtual env of this warp
   const int A = dm.a1, ab = copy * dm.a1, tb = copy * dm.t1, n_targets = dm.t1;
-  double reward[MJB_MAX_AGENTS];
-  bool done[MJB_MAX_AGENTS];
-  int opos[MJB_MAX_AGENTS];
+  double reward[AMAX];
+  bool done[AMAX];
+  int opos[AMAX];
   if (is_reset)  // data_store = {agent: {}} (mujoco_rl.py:312); the draw counter is not part of the store
-    MJB_NOUNROLL
-    for (int a = 0; a < A; a++) {
+    MJB_AGENT_LOOP
+    for (int a = 0; a < AMAX; a++) if (a < A) {
       MJB_NOUNROLL
       for (int k = 0; k < dm.store_i32; k++) if (k != MJB_STORE_I_DRAWS) si[a * dm.store_i32 + k] = 0;
       MJB_NOUNROLL
       for (int k = 0; k < dm.store_f32; k++) sf[a * dm.store_f32 + k] = 0.f;
     }
-  MJB_NOUNROLL
-  for (int a = 0; a < A; a++) { reward[a] = 0.0; done[a] = false; opos[a] = dm.obs_adr[ab + a + 1] - dm.obs_adr[ab + a]; }
+  MJB_AGENT_LOOP
+  for (int a = 0; a < AMAX; a++) if (a < A) { reward[a] = 0.0; done[a] = false; opos[a] = dm.obs_adr[ab + a + 1] - dm.obs_adr[ab + a]; }
   MJB_NOUNROLL
   for (int p = 0; p < dm.n_dynamics; p++) {
     const DevPlugin& dyn = dm.dynamics[p];
-    MJB_NOUNROLL
-    for (int a = 0; a < A; a++) {
+    MJB_AGENT_LOOP
+    for (int a = 0; a < AMAX; a++) if (a < A) {
       int* sia = si + a * dm.store_i32;
       float* sfa = sf + a * dm.store_f32;
       float* oa = obs + a * dm.obs_stride;
@@ -102,8 +112,8 @@ MJB_DEV void run_plugins(const DevModel& dm, const float* ctrl, float* obs, floa
   }
   if (is_reset) {
     // everything the dynamics wrote is discarded (mujoco_rl.py:326-328); rewards / dones are not run
-    MJB_NOUNROLL
-    for (int a = 0; a < A; a++) {
+    MJB_AGENT_LOOP
+    for (int a = 0; a < AMAX; a++) if (a < A) {
       MJB_NOUNROLL
       for (int k = 0; k < dm.store_i32; k++) if (k != MJB_STORE_I_DRAWS) si[a * dm.store_i32 + k] = 0;
       MJB_NOUNROLL
@@ -117,8 +127,8 @@ MJB_DEV void run_plugins(const DevModel& dm, const float* ctrl, float* obs, floa
   MJB_NOUNROLL
   for (int p = 0; p < dm.n_rewards; p++) {
     const DevPlugin& rf = dm.rewards[p];
-    MJB_NOUNROLL
-    for (int a = 0; a < A; a++) {
+    MJB_AGENT_LOOP
+    for (int a = 0; a < AMAX; a++) if (a < A) {
       int* sia = si + a * dm.store_i32;
       float* sfa = sf + a * dm.store_f32;
       if (rf.kind == MJB_REW_TAG_DISTANCE) {
@@ -157,14 +167,14 @@ MJB_DEV void run_plugins(const DevModel& dm, const float* ctrl, float* obs, floa
   MJB_NOUNROLL
   for (int p = 0; p < dm.n_dones && !all; p++) {
     const DevPlugin& df = dm.dones[p];
-    MJB_NOUNROLL
-    for (int a = 0; a < A; a++)
+    MJB_AGENT_LOOP
+    for (int a = 0; a < AMAX; a++) if (a < A)
       if (df.kind == MJB_DONE_DISTANCE_LE) done[a] = done[a] || (ld_dist(sf + a * dm.store_f32) <= (double)df.param[0]);
-    MJB_NOUNROLL
-    for (int a = 0; a < A; a++) all = all || done[a];
+    MJB_AGENT_LOOP
+    for (int a = 0; a < AMAX; a++) if (a < A) all = all || done[a];
   }
-  MJB_NOUNROLL
-  for (int a = 0; a < A; a++) { rew[a] = (float)reward[a]; term[a] = done[a] ? 1 : 0; }
+  MJB_AGENT_LOOP
+  for (int a = 0; a < AMAX; a++) if (a < A) { rew[a] = (float)reward[a]; term[a] = done[a] ? 1 : 0; }
   term[A] = all ? 1 : 0;
   *ts_io = ts + 1;
 }
@@ -180,11 +190,13 @@ MJB_DEV void split_copy(int i, int n1, int K, int& k, int& j) {
 // model with `pack` independent copies (csrc/replicate.h); pack == 1 is the plain case.  Virtual state index i
 // of a per-copy array of length n1 maps to copy i / n1, element i % n1 of that real env's HBM row.
 template <bool PHYS, bool PACKED>
-MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs, int mode, int skip_frames,
+MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_envs, int mode, int skip_frames,
                      const uint8_t* reset_mask) {
+  Ctx c = c_in;
   float* probe = c.probe;
   const DevModel& dm = *c.dm;
   const int lane = c.lane, K = PACKED ? dm.pack : 1, e0 = venv * K;   // K == 1 folds all copy arithmetic away
+  c.probe_quat = (!PACKED && B.probe_quat) ? B.probe_quat + (size_t)e0 * dm.np1 * 4 : nullptr;
   // which copies hold a real env, and which of them this launch updates
   uint32_t live = 0, upd = 0;
   for (int k = 0; k < K; k++)
@@ -467,7 +479,7 @@ MJB_DEV void run_env(const Ctx& c, const mjb_buffers& B, int venv, int num_envs,
     }
     MJB_SYNC();
     if (lane == 0)
-      run_plugins(dm, SF(ctrl) + k * dm.nu1, B.obs + (size_t)env * A1 * dm.obs_stride, B.reward + (size_t)env * A1, B.term + (size_t)env * (A1 + 1),
+      run_plugins<MJB_MAX_AGENTS>(dm, SF(ctrl) + k * dm.nu1, B.obs + (size_t)env * A1 * dm.obs_stride, B.reward + (size_t)env * A1, B.term + (size_t)env * (A1 + 1),
                   B.trunc + (size_t)env * (A1 + 1), env, k, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
     MJB_SYNC();
     for (int i = lane; i < A1 * dm.store_i32; i += 32) gsi[i] = s_si[i];

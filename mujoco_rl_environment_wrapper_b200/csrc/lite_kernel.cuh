@@ -8,11 +8,15 @@
 //     rows), fetched by one 1-D TMA bulk copy each (cp.async.bulk -> shared memory, one mbarrier for the tile);
 //   * actions scatter, observation gather and the plugin programme run out of shared memory (thread = env for the
 //     scatter and the reference-order plugin programme, warp = env / lane = word for the gather);
-//   * results leave as 128-bit coalesced stores of whole row blocks; only what the step changes is written
-//     (qvel or ctrl, obs, reward, flags, data_store rows, step counter);
-//   * no model image staging: the two index tables are copied into shared memory once per CTA, under the first load.
+//   * observations are gathered straight into HBM (consecutive threads write consecutive words of a row); the other
+//     results leave as 128-bit stores of whole row blocks; only what the step changes is written (qvel or ctrl, obs,
+//     reward, flags, data_store rows, step counter);
+//   * no model image staging: the two index tables (built on the host) ride in on the first tile's bulk copies.
 // Several small CTAs per SM keep tens of KB of loads in flight per SM.
 #pragma once
+#include <cstdio>
+#include <vector>
+
 #include "env_kernel.cuh"
 #include "tma_prims.cuh"
 
@@ -27,7 +31,11 @@ struct LiteLayout {
   // word offsets of the tile arrays in dynamic shared memory (after the 16-byte barrier slot)
   int o_qpos, o_qvel, o_ctrl, o_sens, o_act, o_probe, o_si, o_sf, o_ts, o_obs, o_rew, o_term, o_trunc;
   int o_gather, o_actidx;         // per-CTA copies of the two index tables (one entry per obs-row word / physical action)
+  int table_words;                // gather table + action table, contiguous (o_gather .. ), multiple of 4
+  int o_dm, dm_bytes;             // shared-memory copy of the DevModel header (the plugin programme reads it a lot)
+  int A, qs, vs, cs, ss, as, ps, sis, sfs;   // agents and row strides in words (what thread 0 needs to issue the loads)
   int words;
+  int profile;                    // MJB_LITE_PROFILE=1: CTA 0 prints the clock cycles of its phases (debug)
 };
 
 inline LiteLayout make_lite_layout(const DevModel& dm, int tile) {
@@ -44,13 +52,36 @@ inline LiteLayout make_lite_layout(const DevModel& dm, int tile) {
   L.o_ctrl = take(L.use_ctrl ? dm.ctrl_stride : 0); L.o_sens = take(L.use_sens ? dm.sensor_stride : 0);
   L.o_act = take(A * dm.act_stride); L.o_probe = take(L.use_probe ? dm.np1 * 4 : 0);
   L.o_si = take(A * dm.store_i32); L.o_sf = take(A * dm.store_f32); L.o_ts = take(1);
-  L.o_obs = take(L.per_obs); L.o_rew = take(A);
+  L.o_obs = o; L.o_rew = take(A);   // observations are not staged: gathered straight into HBM
   L.o_term = o; o += ((tile * (A + 1) + 15) / 16) * 4;
   L.o_trunc = o; o += ((tile * (A + 1) + 15) / 16) * 4;
   L.o_gather = o; o += ((L.per_obs + 3) / 4) * 4;
   L.o_actidx = o; o += ((A * dm.n_phys_act + 3) / 4) * 4;
+  L.table_words = o - L.o_gather;
+  L.o_dm = o; L.dm_bytes = (int)((sizeof(DevModel) + 15) / 16 * 16); o += L.dm_bytes / 4;
+  L.A = A; L.qs = dm.qpos_stride; L.vs = dm.qvel_stride; L.cs = dm.ctrl_stride; L.ss = dm.sensor_stride; L.as = A * dm.act_stride;
+  L.ps = dm.np1 * 4; L.sis = A * dm.store_i32; L.sfs = A * dm.store_f32;
   L.words = o;
   return L;
+}
+
+__device__ __noinline__ void lite_report(const long long* t) {
+  printf("k_lite cta0 cycles: tables+issue %lld | load wait %lld | scatter %lld | gather %lld | plugins %lld | stores %lld\n", t[1] - t[0], t[2] - t[1],
+         t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5]);
+}
+
+// the two index tables in the kernel's shared-memory order: entry r of an env's obs rows -> (kind << 24 | address) or
+// -1 for row padding, then the qvel / ctrl address of every physical action
+inline std::vector<int> lite_tables(const DevModel& dm, const LiteLayout& L, const uint32_t* image) {
+  std::vector<int> t(L.table_words, 0);
+  const int* obs_index = reinterpret_cast<const int*>(image + dm.off[IF_obs_index]);
+  const int* act_index = reinterpret_cast<const int*>(image + dm.off[IF_act_index]);
+  for (int r = 0; r < L.per_obs; r++) {
+    const int a = r / dm.obs_stride, k = r - a * dm.obs_stride;
+    t[r] = k < dm.obs_adr[a + 1] - dm.obs_adr[a] ? obs_index[dm.obs_adr[a] + k] : -1;
+  }
+  for (int k = 0; k < dm.a1 * dm.n_phys_act; k++) t[(L.o_actidx - L.o_gather) + k] = act_index[k];
+  return t;
 }
 
 // 128-bit copy of `words` floats (multiple of 4; both sides 16-byte aligned) from shared to global memory
@@ -60,55 +91,74 @@ __device__ __forceinline__ void tile_store(float* __restrict__ dst, const float*
   for (int i = tid; i < (words >> 2); i += nthreads) d4[i] = s4[i];
 }
 
-__global__ void __launch_bounds__(LITE_THREADS, 8) k_lite(const __grid_constant__ DevModel dm, const uint32_t* __restrict__ image, const mjb_buffers B,
-                                              const LiteLayout L, int active, int env_base) {
+// Kernel parameters are kept small (layout + pointers): the DevModel header travels through global memory into shared
+// memory with the first tile, so that a cold start touches two parameter cache lines instead of a dozen.
+__global__ void __launch_bounds__(LITE_THREADS, 8) k_lite(const DevModel* __restrict__ dm_global, const __grid_constant__ mjb_buffers B, const __grid_constant__ LiteLayout L,
+                                                         const int* __restrict__ tables, int active, int env_base) {
   extern __shared__ __align__(128) uint32_t lite_smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(lite_smem);
   float* sm = reinterpret_cast<float*>(lite_smem + 4);
   float *s_qpos = sm + L.o_qpos, *s_qvel = sm + L.o_qvel, *s_ctrl = sm + L.o_ctrl, *s_sens = sm + L.o_sens, *s_act = sm + L.o_act;
-  float *s_probe = sm + L.o_probe, *s_sf = sm + L.o_sf, *s_obs = sm + L.o_obs, *s_rew = sm + L.o_rew;
+  float *s_probe = sm + L.o_probe, *s_sf = sm + L.o_sf, *s_rew = sm + L.o_rew;
   int *s_si = reinterpret_cast<int*>(sm + L.o_si), *s_ts = reinterpret_cast<int*>(sm + L.o_ts);
   uint8_t *s_term = reinterpret_cast<uint8_t*>(sm + L.o_term), *s_trunc = reinterpret_cast<uint8_t*>(sm + L.o_trunc);
-  const int tid = threadIdx.x, nthreads = blockDim.x, T = L.tile, A = dm.a1;
+  const DevModel& dm = *reinterpret_cast<const DevModel*>(sm + L.o_dm);   // valid after the first barrier wait
+  const int tid = threadIdx.x, nthreads = blockDim.x, T = L.tile, A = L.A;
   int *s_gather = reinterpret_cast<int*>(sm + L.o_gather), *s_actidx = reinterpret_cast<int*>(sm + L.o_actidx);
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-  // the index tables, once per CTA: entry r of an env's obs rows -> (kind << 24 | address) or -1 for row padding
-  {
-    const int* act_index = reinterpret_cast<const int*>(image + dm.off[IF_act_index]);
-    const int* obs_index = reinterpret_cast<const int*>(image + dm.off[IF_obs_index]);
-    for (int r = tid; r < L.per_obs; r += nthreads) {
-      const int a = r / dm.obs_stride, k = r - a * dm.obs_stride;
-      s_gather[r] = k < dm.obs_adr[a + 1] - dm.obs_adr[a] ? __ldg(obs_index + dm.obs_adr[a] + k) : -1;
-    }
-    for (int k = tid; k < A * dm.n_phys_act; k += nthreads) s_actidx[k] = __ldg(act_index + k);
+  // cold start: touch every cache line of the kernel parameters at once (lanes in parallel) instead of one miss after
+  // the other as the code first needs them
+  if (tid < 4) {
+    const int* pw = reinterpret_cast<const int*>(&B);
+    int touch = pw[min(tid * 32, (int)((sizeof(mjb_buffers) + sizeof(LiteLayout)) / 4) - 1)];
+    asm volatile("" ::"r"(touch));
   }
+  long long tk[7];
+  const bool prof = L.profile && blockIdx.x == 0 && tid == 0;
+  if (prof) tk[0] = clock64();
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncthreads();
+  bool first = true;   // the first tile's barrier also covers the two index tables (built on the host, lite_tables())
   const int ntiles = (active + T - 1) / T;
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, phase ^= 1u) {
     const int n = min(T, active - tile * T);          // envs of this tile
     const size_t e0 = (size_t)env_base + (size_t)tile * T;
-    if (tid == 0) {
-      // the previous tile's shared-memory reads / writes (generic proxy) are ordered before the bulk copies (async proxy)
+    if (tid < 32) {
+      // the previous tile's shared-memory reads / writes (generic proxy) are ordered before the bulk copies (async proxy);
+      // lane k of warp 0 issues copy k, lane 0 also posts the byte count (complete_tx may legally run ahead of it)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       const uint32_t row = 4u * (uint32_t)n;
-      uint32_t bytes = row * (dm.qpos_stride + dm.qvel_stride + A * dm.act_stride + A * dm.store_i32 + A * dm.store_f32);
-      if (L.use_ctrl) bytes += row * dm.ctrl_stride;
-      if (L.use_sens) bytes += row * dm.sensor_stride;
-      if (L.use_probe) bytes += row * dm.np1 * 4;
-      mbar_expect_tx(bar, bytes);
-      bulk_g2s(s_qpos, B.qpos + e0 * dm.qpos_stride, row * dm.qpos_stride, bar);
-      bulk_g2s(s_qvel, B.qvel + e0 * dm.qvel_stride, row * dm.qvel_stride, bar);
-      if (L.use_ctrl) bulk_g2s(s_ctrl, B.ctrl + e0 * dm.ctrl_stride, row * dm.ctrl_stride, bar);
-      if (L.use_sens) bulk_g2s(s_sens, B.sensordata + e0 * dm.sensor_stride, row * dm.sensor_stride, bar);
-      bulk_g2s(s_act, B.actions + e0 * A * dm.act_stride, row * A * dm.act_stride, bar);
-      if (L.use_probe) bulk_g2s(s_probe, B.probe + e0 * dm.np1 * 4, row * dm.np1 * 4, bar);
-      bulk_g2s(s_si, B.store_i + e0 * A * dm.store_i32, row * A * dm.store_i32, bar);
-      bulk_g2s(s_sf, B.store_f + e0 * A * dm.store_f32, row * A * dm.store_f32, bar);
+      void* dst = nullptr;
+      const void* src = nullptr;
+      uint32_t nb = 0;
+      switch (tid) {
+        case 0: dst = s_qpos; src = B.qpos + e0 * L.qs; nb = row * L.qs; break;
+        case 1: dst = s_qvel; src = B.qvel + e0 * L.vs; nb = row * L.vs; break;
+        case 2: dst = s_act; src = B.actions + e0 * L.as; nb = row * L.as; break;
+        case 3: dst = s_si; src = B.store_i + e0 * L.sis; nb = row * L.sis; break;
+        case 4: dst = s_sf; src = B.store_f + e0 * L.sfs; nb = row * L.sfs; break;
+        case 5: if (L.use_ctrl) { dst = s_ctrl; src = B.ctrl + e0 * L.cs; nb = row * L.cs; } break;
+        case 6: if (L.use_sens) { dst = s_sens; src = B.sensordata + e0 * L.ss; nb = row * L.ss; } break;
+        case 7: if (L.use_probe) { dst = s_probe; src = B.probe + e0 * L.ps; nb = row * L.ps; } break;
+        case 8: if (first) { dst = s_gather; src = tables; nb = 4u * (uint32_t)L.table_words; } break;
+        case 9: if (first) { dst = sm + L.o_dm; src = dm_global; nb = (uint32_t)L.dm_bytes; } break;
+        default: break;
+      }
+      if (tid == 0) {
+        uint32_t bytes = row * (L.qs + L.vs + L.as + L.sis + L.sfs);
+        if (L.use_ctrl) bytes += row * L.cs;
+        if (L.use_sens) bytes += row * L.ss;
+        if (L.use_probe) bytes += row * L.ps;
+        if (first) bytes += 4u * (uint32_t)L.table_words + (uint32_t)L.dm_bytes;
+        mbar_expect_tx(bar, bytes);
+      }
+      if (nb) bulk_g2s(dst, src, nb, bar);
     }
     for (int e = tid; e < n; e += nthreads) s_ts[e] = B.timestep[e0 + e];   // 4 bytes per env: not worth a bulk copy (alignment of odd ranges)
+    first = false;
+    if (prof) tk[1] = clock64();
     mbar_wait(bar, phase);
+    if (prof) tk[2] = clock64();
     // apply_action (mujoco_parent.py:316-332): overwrite qvel (freeJoint) or ctrl; thread = env
     for (int e = tid; e < n; e += nthreads) {
       float* dst = dm.free_joint ? s_qvel + e * dm.qvel_stride : s_ctrl + e * dm.ctrl_stride;
@@ -117,24 +167,46 @@ __global__ void __launch_bounds__(LITE_THREADS, 8) k_lite(const __grid_constant_
         for (int j = 0; j < dm.n_phys_act; j++, k++) dst[s_actidx[k]] = src[a * dm.act_stride + j];
     }
     __syncthreads();
-    // get_observations (mujoco_parent.py:380-392): warp = env, lane = word of its obs rows; padding is written as zero
-    for (int e = warp; e < n; e += nwarps) {
-      const float *q = s_qpos + e * dm.qpos_stride, *v = s_qvel + e * dm.qvel_stride, *sd = s_sens + e * dm.sensor_stride;
-      for (int r = lane; r < L.per_obs; r += 32) {
-        const int ent = s_gather[r], kind = ent >> 24, adr = ent & 0xffffff;
-        s_obs[e * L.per_obs + r] = ent < 0 ? 0.f : (kind == 0 ? sd[adr] : (kind == 1 ? q[adr] : v[adr]));
+    if (prof) tk[3] = clock64();
+    // get_observations (mujoco_parent.py:380-392): thread = (word r of the obs rows, group of eight envs): one table read,
+    // eight independent loads
+    const int ngrp = (n + 7) >> 3;
+    for (int i = tid; i < L.per_obs * ngrp; i += nthreads) {
+      const int g = i / L.per_obs, r = i - g * L.per_obs, e = g << 3, m = min(8, n - e);
+      const int ent = s_gather[r], kind = ent >> 24, adr = ent & 0xffffff;
+      float* dst = B.obs + (e0 + e) * L.per_obs + r;   // consecutive threads -> consecutive words of a row: full-line stores
+      if (ent < 0) {
+        for (int u = 0; u < m; u++) dst[u * L.per_obs] = 0.f;
+      } else {
+        const int st = kind == 0 ? dm.sensor_stride : (kind == 1 ? dm.qpos_stride : dm.qvel_stride);
+        const float* src = (kind == 0 ? s_sens : (kind == 1 ? s_qpos : s_qvel)) + adr + e * st;
+        if (m == 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = src[u * st];
+#pragma unroll
+          for (int u = 0; u < 8; u++) dst[u * L.per_obs] = v[u];
+        } else {
+          for (int u = 0; u < m; u++) dst[u * L.per_obs] = src[u * st];
+        }
       }
     }
     __syncthreads();
+    if (prof) tk[4] = clock64();
     // dynamics / reward / truncation / done in the reference's order: thread = env, on its rows in shared memory
     for (int e = tid; e < n; e += nthreads) {
-      run_plugins(dm, s_ctrl + e * dm.ctrl_stride, s_obs + e * L.per_obs, s_rew + e * A, s_term + e * (A + 1), s_trunc + e * (A + 1),
+      if (A <= 2)
+        run_plugins<2>(dm, s_ctrl + e * dm.ctrl_stride, B.obs + (e0 + e) * L.per_obs, s_rew + e * A, s_term + e * (A + 1), s_trunc + e * (A + 1),
+                       (int)e0 + e, 0, false, s_probe + e * dm.np1 * 4, s_si + e * A * dm.store_i32, s_sf + e * A * dm.store_f32,
+                       s_act + e * A * dm.act_stride, s_ts + e);
+      else
+      run_plugins<MJB_MAX_AGENTS>(dm, s_ctrl + e * dm.ctrl_stride, B.obs + (e0 + e) * L.per_obs, s_rew + e * A, s_term + e * (A + 1), s_trunc + e * (A + 1),
                   (int)e0 + e, 0, false, s_probe + e * dm.np1 * 4, s_si + e * A * dm.store_i32, s_sf + e * A * dm.store_f32,
                   s_act + e * A * dm.act_stride, s_ts + e);
     }
     __syncthreads();
+    if (prof) tk[5] = clock64();
     // results: whole row blocks, 128-bit stores
-    tile_store(B.obs + e0 * L.per_obs, s_obs, n * L.per_obs, tid, nthreads);
     if (dm.free_joint) tile_store(B.qvel + e0 * dm.qvel_stride, s_qvel, n * dm.qvel_stride, tid, nthreads);
     else tile_store(B.ctrl + e0 * dm.ctrl_stride, s_ctrl, n * dm.ctrl_stride, tid, nthreads);
     tile_store(reinterpret_cast<float*>(B.store_i + e0 * A * dm.store_i32), reinterpret_cast<const float*>(s_si), n * A * dm.store_i32, tid, nthreads);
@@ -143,6 +215,7 @@ __global__ void __launch_bounds__(LITE_THREADS, 8) k_lite(const __grid_constant_
     for (int i = tid; i < n * (A + 1); i += nthreads) { B.term[e0 * (A + 1) + i] = s_term[i]; B.trunc[e0 * (A + 1) + i] = s_trunc[i]; }
     for (int e = tid; e < n; e += nthreads) B.timestep[e0 + e] = s_ts[e];
     __syncthreads();
+    if (prof) { tk[6] = clock64(); lite_report(tk); }
   }
 }
 

@@ -96,6 +96,8 @@ struct mjb_batch {
   mjb::LiteLayout tile{};   // skipFrames = 0: tile kernel geometry
   int tile_grid = 0;
   size_t tile_smem = 0;
+  int* d_lite_tab = nullptr;   // the tile kernel's index tables (lite_tables())
+  mjb::DevModel* d_lite_dm = nullptr;   // ... and its DevModel header, padded to 16 bytes
   mjb_buffers B;
   int num_envs = 0, device = 0, warps = 0, grid = 0;
   size_t smem_bytes = 0;
@@ -154,7 +156,7 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStr
   if (mode == mjb::MODE_STEP && b->has_lite && !b->subset) {
     // no physics in the step: the bandwidth-shaped tile kernel (lite_kernel.cuh) over the contiguous env range
     const int ntiles = (active + b->tile.tile - 1) / b->tile.tile;
-    mjb::k_lite<<<std::min(ntiles, b->tile_grid), LITE_THREADS, b->tile_smem, stream>>>(b->lite.dm, b->d_image, B, b->tile, active, base);
+    mjb::k_lite<<<std::min(ntiles, b->tile_grid), LITE_THREADS, b->tile_smem, stream>>>(b->d_lite_dm, B, b->tile, b->d_lite_tab, active, base);
   } else if (mode == mjb::MODE_STEP && b->has_lite) {
     // an env-id list (level variants) is not a contiguous range: the warp-per-env form of the same step
     mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, stream>>>(b->lite.dm, b->d_image, B, b->num_envs, mode,
@@ -279,6 +281,7 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     int tile = std::max(16, mjb::env_int("MJB_LITE_TILE", 64) / 16 * 16);
     for (;;) {
       b->tile = mjb::make_lite_layout(b->lite.dm, tile);
+      b->tile.profile = mjb::env_int("MJB_LITE_PROFILE", 0);
       b->tile_smem = 16 + (size_t)b->tile.words * 4;
       if (b->tile_smem <= 48 * 1024 || tile <= 16) break;
       tile /= 2;
@@ -290,6 +293,18 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
       return fail(MJB_ERR_CUDA);
     }
     b->tile_grid = prop.multiProcessorCount * tile_per_sm;
+    {
+      std::vector<int> tab = mjb::lite_tables(b->lite.dm, b->tile, b->img.words.data());
+      std::vector<char> hdr(b->tile.dm_bytes, 0);
+      memcpy(hdr.data(), &b->lite.dm, sizeof(mjb::DevModel));
+      if (cudaMalloc(&b->d_lite_tab, tab.size() * 4) != cudaSuccess ||
+          cudaMemcpy(b->d_lite_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMalloc(&b->d_lite_dm, hdr.size()) != cudaSuccess ||
+          cudaMemcpy(b->d_lite_dm, hdr.data(), hdr.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        mjb::set_error("tile kernel table upload failed");
+        return fail(MJB_ERR_CUDA);
+      }
+    }
   }
   if (cudaMalloc(&b->d_image, (size_t)dm.image_words * 4) != cudaSuccess ||
       cudaMemcpy(b->d_image, b->img.words.data(), (size_t)dm.image_words * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -335,6 +350,8 @@ void mjb_batch_destroy(mjb_batch* b) {
   if (b->d_rimage) cudaFree(b->d_rimage);
   if (b->d_rtab) cudaFree(b->d_rtab);
   if (b->d_next) cudaFree(b->d_next);
+  if (b->d_lite_tab) cudaFree(b->d_lite_tab);
+  if (b->d_lite_dm) cudaFree(b->d_lite_dm);
   if (b->h_first) cudaFreeHost(b->h_first);
   if (b->h_act) cudaFreeHost(b->h_act);
   if (b->h_obs) cudaFreeHost(b->h_obs);

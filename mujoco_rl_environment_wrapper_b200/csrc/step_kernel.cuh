@@ -87,6 +87,7 @@ struct Ctx {
   float* probe;         // exported positions of this env (shared memory, 4 floats per probe)
   int cta_threads;      // threads of the CTA busy in this lock-step round (0 / 32: no CTA-level alignment)
   int align_all;        // 1: also align around constraints / Newton iterations; 0: only before the collision phase
+  float* probe_quat;    // this env's exported orientations in GLOBAL memory (4 floats per probe) or null
 };
 #define CI(f) ((const int*)(c.img + c.dm->off[IF_##f]))
 #define CU(f) ((const uint32_t*)(c.img + c.dm->off[IF_##f]))
@@ -1447,6 +1448,18 @@ MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out, int
       int kind = CI(probe_kind)[p], id = CI(probe_id)[p];
       f3 v = kind == PROBE_BODY ? ld3(SF(xipos) + 3 * id) : (kind == PROBE_GEOM ? ld3(SF(gpos) + 3 * id) : ld3(CF(probe_const) + 3 * p));
       c.probe[4 * p] = v.x; c.probe[4 * p + 1] = v.y; c.probe[4 * p + 2] = v.z; c.probe[4 * p + 3] = 0.f;
+      if (c.probe_quat && kind != PROBE_CONST) {
+        // orientation of the body frame (data.body(n).xmat) / of the geom frame (data.geom(n).xmat), as a quaternion
+        q4 q;
+        if (kind == PROBE_BODY) q = ldq(SF(xquat) + 4 * id);
+        else {
+          int g = 0;   // geom id of the dynamic slot
+          MJB_NOUNROLL
+          for (int k = 0; k < dm.ngeom; k++) if (CI(geom_slot)[k] == id) g = k;
+          q = qnorm(qmul(ldq(SF(xquat) + 4 * CI(geom_mb)[g]), ldq(CF(geom_quat) + 4 * g)));
+        }
+        c.probe_quat[4 * p] = q.w; c.probe_quat[4 * p + 1] = q.x; c.probe_quat[4 * p + 2] = q.y; c.probe_quat[4 * p + 3] = q.z;
+      }
     }
     MJB_SYNC();
   }

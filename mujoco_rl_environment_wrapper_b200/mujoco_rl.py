@@ -22,6 +22,8 @@ import torch
 
 from . import _lib as L
 from .batch import Batch
+from .dataview import DataView, ModelView, quat_to_euler_zyx_deg, static_pose
+from .plugins import recognise
 from .spaces import Box
 from .tables import Tables
 
@@ -72,6 +74,12 @@ class MuJoCoRL:
         self.num_envs = int(config_dict.get("num_envs", 1))
         self.seed = int(config_dict.get("seed", 1234))
         self.reset_noise = float(config_dict.get("resetNoise", 0.0))   # new, off: the reference restarts at qpos0
+        # new: names of further bodies / geoms whose positions (and orientations) are exported every step, or "all";
+        # agents, "target"-tagged objects and static objects are always available to distance / get_data / data.body(n)
+        self.export_positions = config_dict.get("exportPositions", [])
+        # orientations of the exported moving objects (get_data()["orientation"]); default: on for the drop-in
+        # single env, off for batches (16 bytes per object and env-step)
+        self.export_orientation = bool(config_dict.get("exportOrientation", self.num_envs == 1 or bool(self.export_positions)))
         dev = config_dict.get("device", None)
         if not torch.cuda.is_available():
             raise RuntimeError("MuJoCoRL (B200): no CUDA device available; this implementation has no CPU fallback")
@@ -93,7 +101,7 @@ class MuJoCoRL:
         for path in self._level_paths:
             with open(path, "r") as fh:
                 text = fh.read()
-            model = L.Model(text)
+            model = ModelView(L.Model(text))
             tables = Tables(text, model, self.agents, self.free_joint)
             info_json, names = self.__load_json(path)
             self._levels.append({"xml_path": path, "xml_text": text, "model": model, "tables": tables,
@@ -112,12 +120,20 @@ class MuJoCoRL:
         self.agents_observation_index = self._tables.agents_observation_index
 
         self.data_store = {agent: AgentStore(self, a) for a, agent in enumerate(self.agents)}
+        self.data = DataView(self)
         self.environment_dynamics = [dyn(self) for dyn in dynamics_classes]
         self.__build_spaces()
         self.__build_batch()
-        self.__check_dynamics(self.environment_dynamics)
-        self.__check_reward_functions(self.reward_functions)
-        self.__check_done_functions(self.done_functions)
+        # the reference validates every plugin by calling it once (mujoco_rl.py:114-169); whatever that call writes is
+        # discarded again (store, draw counters), so that construction does not consume random draws
+        b = self._batch
+        snap = (b.store_i.clone(), b.store_f.clone())
+        # (plugins fused through their verbatim reference source are not called: their code is written for one env)
+        own = lambda obj: hasattr(obj, "mjb_kind")
+        self.__check_dynamics([d for d in self.environment_dynamics if d not in self._fused_dyn or own(d.__class__)])
+        self.__check_reward_functions([fn for fn in self.reward_functions if fn in self._host_rew or own(fn)])
+        self.__check_done_functions([fn for fn in self.done_functions if fn in self._host_done or own(fn)])
+        b.store_i.copy_(snap[0]); b.store_f.copy_(snap[1])
         self._wipe_store()
 
     # ------------------------------------------------------------------------------------------
@@ -209,7 +225,7 @@ class MuJoCoRL:
             lv["spec"], lv["target_names"], lv["probe_names"] = spec, self._target_names, self._probe_names
             with torch.cuda.device(self.device):
                 lv["batch"] = Batch(self.model, spec, self.num_envs, device=self.device, keepalive=keep,
-                                    share=self._levels[0]["batch"] if lid else None)
+                                    share=self._levels[0]["batch"] if lid else None, probe_quat=self.export_orientation)
         self._use_level(0)
         self._spec, self._batch = self._levels[0]["spec"], self._levels[0]["batch"]
         self.level_id = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
@@ -260,34 +276,36 @@ class MuJoCoRL:
         nd = nr = ndn = 0
         act_pos = n_phys
         fused_obs = 0
+        # a plugin is fused when it is one of the reference's examples (marker or verbatim source, plugins.recognise)
+        # and no host plugin precedes it in its list (the lists run in order)
         for dyn in self.environment_dynamics:
-            kind = getattr(dyn, "mjb_kind", None)
+            kind = recognise(dyn.__class__)
             lo = act_pos
             act_pos += len(dyn.action_space["low"])
             if kind and kind[0] == "dynamic" and not self._host_dyn:
                 p = spec.dynamics[nd]
                 p.kind, p.act_lo, p.act_hi, p.n_obs = kind[1], lo, act_pos, len(dyn.observation_space["low"])
-                p.param[0] = float(getattr(dyn, "threshold", 0.0))
+                p.param[0] = float(getattr(dyn, "threshold", kind[2].get("threshold", 0.0)))
                 nd += 1
                 fused_obs += p.n_obs
                 self._fused_dyn.append(dyn)
             else:
                 self._host_dyn.append((dyn, lo, act_pos))
         for fn in self.reward_functions:
-            kind = getattr(fn, "mjb_kind", None)
+            kind = recognise(fn)
             if kind and kind[0] == "reward" and not self._host_rew:
                 p = spec.rewards[nr]
                 p.kind = kind[1]
-                p.param[0] = float(getattr(fn, "scale", 1.0))
+                p.param[0] = float(getattr(fn, "scale", kind[2].get("scale", 1.0)))
                 nr += 1
             else:
                 self._host_rew.append(fn)
         for fn in self.done_functions:
-            kind = getattr(fn, "mjb_kind", None)
+            kind = recognise(fn)
             if kind and kind[0] == "done" and not self._host_done:
                 p = spec.dones[ndn]
                 p.kind = kind[1]
-                p.param[0] = float(getattr(fn, "threshold", 1.0))
+                p.param[0] = float(getattr(fn, "threshold", kind[2].get("threshold", 1.0)))
                 ndn += 1
             else:
                 self._host_done.append(fn)
@@ -307,6 +325,28 @@ class MuJoCoRL:
             ot, oid = self._resolve(name)
             spec.target_objtype[t], spec.target_objid[t] = ot, oid
             self._probe_names.append(name)
+        extra = self.export_positions
+        if extra == "all":
+            m = self.model
+            extra = [m.id2name(L.OBJ_BODY, i) for i in range(1, m.nbody)] + [m.id2name(L.OBJ_GEOM, i) for i in range(m.ngeom)]
+            extra = [n for n in extra if n]
+        n_x = 0
+        for name in extra:
+            if name in self._probe_names:
+                continue
+            ot, oid = self._resolve(name)
+            if static_pose(self.model.fields, ot, oid) is not None:
+                continue   # static: a constant, needs no slot
+            if n_x >= L.MAX_EXTRA_PROBES:
+                raise Exception(f"at most {L.MAX_EXTRA_PROBES} moving objects can be exported besides agents and targets")
+            spec.extra_objtype[n_x], spec.extra_objid[n_x] = ot, oid
+            self._probe_names.append(name)
+            n_x += 1
+        spec.n_extra_probes = n_x
+        if any((recognise(fn) or (None, None))[:2] == ("reward", L.REW_ANT) for fn in self.reward_functions) and \
+                any(int(t) == 1 for t in self.model.fields["sensor_type"]):
+            raise Exception("ant_reward_function on a model with accelerometer sensors: MuJoCo then fills data.cfrc_ext and the "
+                            "reward's contact-cost term is not zero; this term is not implemented")
         spec.seed = self.seed
         spec.reset_noise = float(self.reset_noise)
         self._ai = (ctypes.c_int32 * max(1, len(act_index)))(*act_index)
@@ -506,15 +546,33 @@ class MuJoCoRL:
         return img if self.num_envs > 1 else img[0].cpu().numpy()
 
     def _position(self, name_or_xyz):
+        """[N, 3] position: exported probe, constant of a static object, or explicit coordinates"""
         if isinstance(name_or_xyz, str):
-            if name_or_xyz not in self._probe_names:
-                raise Exception(f"'{name_or_xyz}' is not an exported position (exported: {self._probe_names}; "
-                                f"agents and objects tagged 'target' in the info JSON)")
-            return self._batch.probe[:, self._probe_names.index(name_or_xyz), :3]
-        return torch.as_tensor(name_or_xyz, dtype=torch.float32, device=self.device).reshape(-1, 3)
+            name = name_or_xyz
+            if name in self._probe_names:
+                return self._batch.probe[:, self._probe_names.index(name), :3]
+            ot, oid = self._resolve(name)
+            sp = static_pose(self.model.fields, ot, oid)
+            if sp is None:
+                raise Exception(f"'{name}' moves and its position is not exported (exported: {self._probe_names}); "
+                                f"add it to config_dict['exportPositions'] (or use \"all\")")
+            return torch.tensor(sp[0], dtype=torch.float32, device=self.device).reshape(1, 3).expand(self.num_envs, 3)
+        return torch.as_tensor(np.asarray(name_or_xyz, dtype=np.float32), device=self.device).reshape(-1, 3)
+
+    def _orientation_quat(self, name):
+        """[N, 4] (w, x, y, z) of the body frame (data.body(n).xmat) or geom frame (data.geom(n).xmat)"""
+        ot, oid = self._resolve(name)
+        sp = static_pose(self.model.fields, ot, oid)
+        if sp is not None:
+            return torch.tensor(sp[1], dtype=torch.float32, device=self.device).reshape(1, 4).expand(self.num_envs, 4)
+        if name in self._probe_names and self._batch.buf.get("probe_quat") is not None:
+            return self._batch.probe_quat[:, self._probe_names.index(name)]
+        raise Exception(f"orientation of '{name}' is not exported: set config_dict['exportOrientation'] = True"
+                        + ("" if name in self._probe_names else " and add it to config_dict['exportPositions']"))
 
     def distance(self, object_1, object_2):
-        d = (self._position(object_1) - self._position(object_2)).norm(dim=1)
+        """mujoco_parent.py:428-449 (math.dist on float64 views): fp64 arithmetic on the fp32 positions"""
+        d = (self._position(object_1).double() - self._position(object_2).double()).pow(2).sum(dim=1).sqrt()
         return d if self.num_envs > 1 else d[0].item()
 
     def collision(self, geom_1, geom_2):
@@ -534,16 +592,21 @@ class MuJoCoRL:
         return r if self.num_envs > 1 else bool(r[0].item())
 
     def get_data(self, name):
+        """mujoco_parent.py:394-426 + mujoco_rl.py:380-395.  `orientation` = zyx Euler angles in degrees of the body /
+        geom frame (helper.py:6-18); None when the object moves and orientations are not exported."""
         ot, oid = self._resolve(name)
         f = self.model.fields
-        pos = self._position(name) if name in self._probe_names else None
-        if pos is not None and self.num_envs == 1:
-            pos = pos[0].cpu().numpy().astype(np.float64)
+        pos = self._out(self._position(name))
+        try:
+            ori = self._out(quat_to_euler_zyx_deg(self._orientation_quat(name)))
+        except Exception:
+            ori = None
         if ot == L.OBJ_BODY:
-            data = {"position": pos, "mass": float(f["body_mass"][oid]), "id": oid, "name": name, "type": "body"}
+            data = {"position": pos, "mass": np.array([f["body_mass"][oid]]) if self.num_envs == 1 else float(f["body_mass"][oid]),
+                    "orientation": ori, "id": oid, "name": name, "type": "body"}
         else:
-            data = {"position": pos, "id": oid, "name": name, "type": "geom",
-                    "color": f["geom_rgba"][4 * oid:4 * oid + 4].copy(), "shape": int(f["geom_type"][oid])}
+            data = {"position": pos, "orientation": ori, "id": oid, "name": name, "type": "geom",
+                    "color": f["geom_rgba"][4 * oid:4 * oid + 4].astype(np.float32), "shape": int(f["geom_type"][oid])}
         if name in self.info_name_list:
             for key, val in self.info_json["environment"]["objects"][name].items():
                 if key not in ["position", "orientation", "mass"]:

@@ -28,7 +28,7 @@ def test_struct_sizes_match_header():
     # the header's structs are POD; sizes computed by hand from the declarations
     assert ctypes.sizeof(L.Plugin) == 32
     assert ctypes.sizeof(L.Layout) == 44
-    assert ctypes.sizeof(L.Buffers) == 20 * 8
+    assert ctypes.sizeof(L.Buffers) == 21 * 8
     assert ctypes.sizeof(L.Dims) == 56
 
 
