@@ -35,7 +35,22 @@ struct LiteLayout {
   int o_dm, dm_bytes;             // shared-memory copy of the DevModel header (the plugin programme reads it a lot)
   int A, qs, vs, cs, ss, as, ps, sis, sfs;   // agents and row strides in words (what thread 0 needs to issue the loads)
   int words;
-  int profile;                    // MJB_LITE_PROFILE=1: CTA 0 prints the clock cycles of its phases (debug)
+  int profile;
+};
+
+// What the start of a tile needs, packed into the FIRST two cache lines of the kernel parameters: a cold launch then
+// waits for one constant-cache fill before its loads are in flight, not for a dozen scattered parameter reads.
+// Copy k: `fixed` bytes from `base` (index tables, DevModel header: first tile of a CTA only) or `row_bytes` per env from
+// `base + env * row_bytes`, to shared-memory byte offset `dst_off`.
+struct LiteCopy {
+  const char* base;
+  uint32_t row_bytes, fixed, dst_off, pad;
+};
+struct LiteIssue {
+  uint32_t sum_row_bytes, first_bytes;
+  int tile, active, env_base, ncopy;
+  int profile, pad;               // MJB_LITE_PROFILE=1: CTA 0 prints the clock cycles of its phases (debug)
+  LiteCopy c[10];
 };
 
 inline LiteLayout make_lite_layout(const DevModel& dm, int tile) {
@@ -91,32 +106,27 @@ __device__ __forceinline__ void tile_store(float* __restrict__ dst, const float*
   for (int i = tid; i < (words >> 2); i += nthreads) d4[i] = s4[i];
 }
 
-// Kernel parameters are kept small (layout + pointers): the DevModel header travels through global memory into shared
-// memory with the first tile, so that a cold start touches two parameter cache lines instead of a dozen.
-__global__ void __launch_bounds__(LITE_THREADS, 8) k_lite(const DevModel* __restrict__ dm_global, const __grid_constant__ mjb_buffers B, const __grid_constant__ LiteLayout L,
-                                                         const int* __restrict__ tables, int active, int env_base) {
+// Kernel parameters: the issue plan first (LiteIssue), then buffers and layout; the DevModel header travels through
+// global memory into shared memory with the first tile.
+__global__ void __launch_bounds__(LITE_THREADS, 8) k_lite(const __grid_constant__ LiteIssue I, const __grid_constant__ mjb_buffers B,
+                                                         const __grid_constant__ LiteLayout L) {
   extern __shared__ __align__(128) uint32_t lite_smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(lite_smem);
   float* sm = reinterpret_cast<float*>(lite_smem + 4);
+  const int tid = threadIdx.x, nthreads = blockDim.x, T = I.tile, active = I.active, env_base = I.env_base;
+  long long tk[7], tx[4] = {0, 0, 0, 0};
+  const bool prof = I.profile && blockIdx.x == 0 && tid == 0;
+  if (prof) tk[0] = clock64();
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (prof) tx[0] = clock64();
   float *s_qpos = sm + L.o_qpos, *s_qvel = sm + L.o_qvel, *s_ctrl = sm + L.o_ctrl, *s_sens = sm + L.o_sens, *s_act = sm + L.o_act;
   float *s_probe = sm + L.o_probe, *s_sf = sm + L.o_sf, *s_rew = sm + L.o_rew;
   int *s_si = reinterpret_cast<int*>(sm + L.o_si), *s_ts = reinterpret_cast<int*>(sm + L.o_ts);
   uint8_t *s_term = reinterpret_cast<uint8_t*>(sm + L.o_term), *s_trunc = reinterpret_cast<uint8_t*>(sm + L.o_trunc);
   const DevModel& dm = *reinterpret_cast<const DevModel*>(sm + L.o_dm);   // valid after the first barrier wait
-  const int tid = threadIdx.x, nthreads = blockDim.x, T = L.tile, A = L.A;
   int *s_gather = reinterpret_cast<int*>(sm + L.o_gather), *s_actidx = reinterpret_cast<int*>(sm + L.o_actidx);
-  // cold start: touch every cache line of the kernel parameters at once (lanes in parallel) instead of one miss after
-  // the other as the code first needs them
-  if (tid < 4) {
-    const int* pw = reinterpret_cast<const int*>(&B);
-    int touch = pw[min(tid * 32, (int)((sizeof(mjb_buffers) + sizeof(LiteLayout)) / 4) - 1)];
-    asm volatile("" ::"r"(touch));
-  }
-  long long tk[7];
-  const bool prof = L.profile && blockIdx.x == 0 && tid == 0;
-  if (prof) tk[0] = clock64();
-  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-  __syncthreads();
+  const int A = L.A;
   bool first = true;   // the first tile's barrier also covers the two index tables (built on the host, lite_tables())
   const int ntiles = (active + T - 1) / T;
   uint32_t phase = 0;
@@ -127,32 +137,16 @@ __global__ void __launch_bounds__(LITE_THREADS, 8) k_lite(const DevModel* __rest
       // the previous tile's shared-memory reads / writes (generic proxy) are ordered before the bulk copies (async proxy);
       // lane k of warp 0 issues copy k, lane 0 also posts the byte count (complete_tx may legally run ahead of it)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const uint32_t row = 4u * (uint32_t)n;
-      void* dst = nullptr;
-      const void* src = nullptr;
-      uint32_t nb = 0;
-      switch (tid) {
-        case 0: dst = s_qpos; src = B.qpos + e0 * L.qs; nb = row * L.qs; break;
-        case 1: dst = s_qvel; src = B.qvel + e0 * L.vs; nb = row * L.vs; break;
-        case 2: dst = s_act; src = B.actions + e0 * L.as; nb = row * L.as; break;
-        case 3: dst = s_si; src = B.store_i + e0 * L.sis; nb = row * L.sis; break;
-        case 4: dst = s_sf; src = B.store_f + e0 * L.sfs; nb = row * L.sfs; break;
-        case 5: if (L.use_ctrl) { dst = s_ctrl; src = B.ctrl + e0 * L.cs; nb = row * L.cs; } break;
-        case 6: if (L.use_sens) { dst = s_sens; src = B.sensordata + e0 * L.ss; nb = row * L.ss; } break;
-        case 7: if (L.use_probe) { dst = s_probe; src = B.probe + e0 * L.ps; nb = row * L.ps; } break;
-        case 8: if (first) { dst = s_gather; src = tables; nb = 4u * (uint32_t)L.table_words; } break;
-        case 9: if (first) { dst = sm + L.o_dm; src = dm_global; nb = (uint32_t)L.dm_bytes; } break;
-        default: break;
+      if (prof) tx[1] = clock64();
+      if (tid == 0) mbar_expect_tx(bar, (uint32_t)n * I.sum_row_bytes + (first ? I.first_bytes : 0u));
+      if (prof) tx[2] = clock64();
+      if (tid < I.ncopy) {
+        const LiteCopy cp = I.c[tid];
+        const uint32_t nb = cp.fixed ? (first ? cp.fixed : 0u) : (uint32_t)n * cp.row_bytes;
+        const char* src = cp.fixed ? cp.base : cp.base + e0 * cp.row_bytes;
+        if (nb) bulk_g2s(reinterpret_cast<char*>(sm) + cp.dst_off, src, nb, bar);
       }
-      if (tid == 0) {
-        uint32_t bytes = row * (L.qs + L.vs + L.as + L.sis + L.sfs);
-        if (L.use_ctrl) bytes += row * L.cs;
-        if (L.use_sens) bytes += row * L.ss;
-        if (L.use_probe) bytes += row * L.ps;
-        if (first) bytes += 4u * (uint32_t)L.table_words + (uint32_t)L.dm_bytes;
-        mbar_expect_tx(bar, bytes);
-      }
-      if (nb) bulk_g2s(dst, src, nb, bar);
+      if (prof) tx[3] = clock64();
     }
     for (int e = tid; e < n; e += nthreads) s_ts[e] = B.timestep[e0 + e];   // 4 bytes per env: not worth a bulk copy (alignment of odd ranges)
     first = false;
@@ -215,7 +209,7 @@ __global__ void __launch_bounds__(LITE_THREADS, 8) k_lite(const DevModel* __rest
     for (int i = tid; i < n * (A + 1); i += nthreads) { B.term[e0 * (A + 1) + i] = s_term[i]; B.trunc[e0 * (A + 1) + i] = s_trunc[i]; }
     for (int e = tid; e < n; e += nthreads) B.timestep[e0 + e] = s_ts[e];
     __syncthreads();
-    if (prof) { tk[6] = clock64(); lite_report(tk); }
+    if (prof) { tk[6] = clock64(); lite_report(tk); printf("  start: init+sync %lld | fence %lld | switch+expect %lld | bulk issue %lld\n", tx[0] - tk[0], tx[1] - tx[0], tx[2] - tx[1], tx[3] - tx[2]); }
   }
 }
 

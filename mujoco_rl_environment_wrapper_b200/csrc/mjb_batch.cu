@@ -156,7 +156,27 @@ int launch(mjb_batch* b, int mode, int skip_frames, const uint8_t* mask, cudaStr
   if (mode == mjb::MODE_STEP && b->has_lite && !b->subset) {
     // no physics in the step: the bandwidth-shaped tile kernel (lite_kernel.cuh) over the contiguous env range
     const int ntiles = (active + b->tile.tile - 1) / b->tile.tile;
-    mjb::k_lite<<<std::min(ntiles, b->tile_grid), LITE_THREADS, b->tile_smem, stream>>>(b->d_lite_dm, B, b->tile, b->d_lite_tab, active, base);
+    const mjb::LiteLayout& T = b->tile;
+    mjb::LiteIssue I{};
+    int k = 0;
+    auto row = [&](const void* basep, int words, int off_words) {
+      if (words <= 0) return;
+      I.c[k].base = (const char*)basep; I.c[k].row_bytes = 4u * words; I.c[k].fixed = 0; I.c[k].dst_off = 4u * off_words; k++;
+      I.sum_row_bytes += 4u * words;
+    };
+    auto fixed = [&](const void* basep, int bytes, int off_words) {
+      I.c[k].base = (const char*)basep; I.c[k].row_bytes = 0; I.c[k].fixed = bytes; I.c[k].dst_off = 4u * off_words; k++;
+      I.first_bytes += bytes;
+    };
+    row(B.qpos, T.qs, T.o_qpos); row(B.qvel, T.vs, T.o_qvel); row(B.actions, T.as, T.o_act);
+    row(B.store_i, T.sis, T.o_si); row(B.store_f, T.sfs, T.o_sf);
+    if (T.use_ctrl) row(B.ctrl, T.cs, T.o_ctrl);
+    if (T.use_sens) row(B.sensordata, T.ss, T.o_sens);
+    if (T.use_probe) row(B.probe, T.ps, T.o_probe);
+    fixed(b->d_lite_tab, 4 * T.table_words, T.o_gather);
+    fixed(b->d_lite_dm, T.dm_bytes, T.o_dm);
+    I.ncopy = k; I.tile = T.tile; I.active = active; I.env_base = base; I.profile = T.profile;
+    mjb::k_lite<<<std::min(ntiles, b->tile_grid), LITE_THREADS, b->tile_smem, stream>>>(I, B, T);
   } else if (mode == mjb::MODE_STEP && b->has_lite) {
     // an env-id list (level variants) is not a contiguous range: the warp-per-env form of the same step
     mjb::k_env<false, false><<<b->lite_grid, b->lite_warps * 32, b->lite_smem, stream>>>(b->lite.dm, b->d_image, B, b->num_envs, mode,
