@@ -32,7 +32,14 @@ MJB_HD uint32_t draw_u32(unsigned long long seed, uint32_t env, uint32_t agent, 
 MJB_DEV double probe_dist(const float* probe, int a, int b) {
   const double dx = (double)probe[4 * a] - (double)probe[4 * b], dy = (double)probe[4 * a + 1] - (double)probe[4 * b + 1],
                dz = (double)probe[4 * a + 2] - (double)probe[4 * b + 2];
-  return sqrt(dx * dx + dy * dy + dz * dz);
+  // plain IEEE evaluation, no fused multiply-add: (dx*dx + dy*dy) + dz*dz, so that any fp64 host evaluation of the same
+  // expression (numpy, torch) gives the same bits
+#if defined(MJB_HOST_EMU)
+  volatile double xx = dx * dx, yy = dy * dy, zz = dz * dz;
+  return sqrt((xx + yy) + zz);
+#else
+  return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+#endif
 }
 MJB_DEV double ld_dist(const float* sfa) {
   union { double d; float f[2]; } u;

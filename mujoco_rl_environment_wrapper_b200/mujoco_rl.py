@@ -387,12 +387,19 @@ class MuJoCoRL:
             if not (isinstance(reward, (int, float)) or torch.is_tensor(reward)):
                 raise Exception(f"Reward, the second return variable of {fn}, must be a float")
 
-    def _wipe_store(self):
+    def _wipe_store(self, mask=None):
+        """data_store = {agent: {}} (mujoco_rl.py:312,328) for all envs or the masked ones; the draw counters are not
+        part of the store"""
         b = self._batch
         keep = b.store_i[:, :, L.STORE_I["draws"]].clone()
-        b.store_i.zero_()
+        if mask is None:
+            b.store_i.zero_()
+            b.store_f.zero_()
+        else:
+            m = mask.to(device=self.device, dtype=torch.bool).reshape(-1)
+            b.store_i[m] = 0
+            b.store_f[m] = 0
         b.store_i[:, :, L.STORE_I["draws"]] = keep
-        b.store_f.zero_()
         for st in self.data_store.values():
             st.clear()
 
@@ -494,8 +501,10 @@ class MuJoCoRL:
                 r, o, d, info = dyn.dynamic(agent, b.actions[:, a, lo:hi])
                 extra[agent].append(torch.as_tensor(o, dtype=torch.float32, device=self.device).reshape(self.num_envs, -1))
                 infos[agent][dyn.__class__.__name__] = info
+        if self._host_dyn:
+            self._wipe_store(mask)   # everything the dynamics wrote is discarded (mujoco_rl.py:326-328) ...
         for st in self.data_store.values():
-            st.clear()  # everything the dynamics wrote is discarded (mujoco_rl.py:326-328)
+            st.clear()               # ... the kernel's reset does the same for the fused ones
         if mask is None:
             self.timestep = 0
         return self._collect_obs(extra), infos
@@ -572,7 +581,8 @@ class MuJoCoRL:
 
     def distance(self, object_1, object_2):
         """mujoco_parent.py:428-449 (math.dist on float64 views): fp64 arithmetic on the fp32 positions"""
-        d = (self._position(object_1).double() - self._position(object_2).double()).pow(2).sum(dim=1).sqrt()
+        v = self._position(object_1).double() - self._position(object_2).double()
+        d = ((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]).sqrt()
         return d if self.num_envs > 1 else d[0].item()
 
     def collision(self, geom_1, geom_2):

@@ -67,7 +67,9 @@ def _dist_to_target(env, a, tgt):
     pr = env._batch.probe.double()
     A = len(env.agents)
     tp = pr[torch.arange(env.num_envs, device=env.device), A + (tgt.long() - 1).clamp(min=0), :3]
-    return (pr[:, a, :3] - tp).pow(2).sum(dim=1).sqrt(), tp
+    d = pr[:, a, :3] - tp
+    # (dx*dx + dy*dy) + dz*dz as separate IEEE operations: the kernel evaluates the same expression without fused multiply-add
+    return ((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]).sqrt(), tp
 
 
 class Language:

@@ -408,7 +408,8 @@ def test_queries_distance_collision_get_data_filter_by_tag():
     assert [t["name"] for t in tg] == ["choice_1", "choice_2"] and tg[0]["type"] == "body" and tg[0]["tags"] == ["target"]
     d = env.distance("sender", "choice_1")
     ref = np.linalg.norm(np.array([-5.522553, 0.9194446, 1.0]) - np.array([7.02852, -2.071592, 0.4710507]))
-    assert torch.allclose(d, torch.full((N,), ref, device="cuda", dtype=torch.float32), rtol=1e-5)
+    assert d.dtype == torch.float64   # the reference's distance is math.dist on float64 views (mujoco_parent.py:449)
+    assert torch.allclose(d, torch.full((N,), ref, device="cuda", dtype=torch.float64), rtol=1e-5)
     assert not bool(env.collision("sender_geom", "choice_1_geom").any())
     for _ in range(400):
         env.step({a: torch.zeros(N, 8) for a in env.agents})

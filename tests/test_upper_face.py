@@ -170,6 +170,7 @@ def test_torch_plugins_equal_the_fused_kernel():
         fused = _env(num_envs=N, seed=9, environmentDynamics=[dyn], rewardFunctions=[P.tag_distance_reward], doneFunctions=[P.distance_done])
         assert host._host_dyn and host._host_rew and host._host_done and fused._spec.n_dynamics == 1
         host.reset(); fused.reset()
+        events = 0
         for t in range(40):
             act = fused.sample_actions()
             host.sample_actions()
@@ -183,7 +184,9 @@ def test_torch_plugins_equal_the_fused_kernel():
                 assert torch.equal(rh[2][a], rf[2][a]) and torch.equal(rh[3][a], rf[3][a])
             assert torch.equal(rh[2]["__all__"], rf[2]["__all__"])
             assert host.batch.store_f.cpu().numpy().tobytes() == fused.batch.store_f.cpu().numpy().tobytes()
-        assert bool(rf[2]["__all__"].any()) or dyn is P.PickUpDynamic
+            assert torch.equal(host.batch.store_i, fused.batch.store_i)
+            events += int(rf[2]["__all__"].sum()) + int(fused.batch.store_i[:, :, L.STORE_I["inventory"]].sum())
+        assert events > 0, "the run must contain done / pick-up events"
 
 
 @pytest.mark.gpu
@@ -191,25 +194,42 @@ def test_get_data_orientation_and_arbitrary_names():
     """get_data()["orientation"] (zyx Euler of xmat, mujoco_parent.py:407,419) and distance() / data.body(n).xipos for objects
     that are neither agents nor targets: static ones are constants, moving ones are exported on request"""
     from oracle import OracleSim
-    env = _env(num_envs=3, exportPositions=["sender_leg_0"] if False else [], exportOrientation=True)
+    env = _env(num_envs=3, exportPositions=["aux_1", "left_ankle_geom"], exportOrientation=True)
     env.reset()
     for _ in range(5):
         env.step(env.sample_actions())
+    # the exported values belong to the LAST forward pass of the step, i.e. to the state before the last integration:
+    # reproduce that with the oracle: mj_forward at the current state equals what the NEXT step exports
     sim = OracleSim(env.model.blob)
     e = 1
     sim.qpos[:] = env.batch.qpos[e, :30].double().cpu().numpy()
+    sim.qvel[:] = env.batch.qvel[e, :28].double().cpu().numpy()
     sim.forward()
+    env.step(env.sample_actions())
     from scipy.spatial.transform import Rotation
-    for name in ("sender", "receiver", "choice_1", "reference"):
+
+    def euler(mat):
+        return Rotation.from_matrix(np.asarray(mat).reshape(3, 3)).as_euler("zyx", degrees=True)   # helper.py:6-18
+
+    m = env.model
+    for name in ("sender", "receiver", "choice_1", "reference", "aux_1"):
         d = env.get_data(name)
-        bid = env.model.name2id(L.OBJ_BODY, name)
-        # positions are those of the last forward pass (pre-integration state): compare orientation on static + the type
-        assert d["type"] == "body" and d["orientation"].shape == (3, 3)
-    stat = env.get_data("reference")
-    rid = env.model.name2id(L.OBJ_BODY, "reference")
-    assert np.abs(stat["position"][e].cpu().numpy() - sim.xipos[rid]).max() < 1e-6
-    want = Rotation.from_matrix(sim.xmat[rid].reshape(3, 3)).as_euler("zyx", degrees=True)
-    assert np.abs(stat["orientation"][e].cpu().numpy() - want).max() < 1e-4
-    assert env.distance("reference", "choice_1").shape == (3,)
+        bid = m.name2id(L.OBJ_BODY, name)
+        assert d["type"] == "body" and d["id"] == bid
+        assert np.abs(d["position"][e].cpu().numpy() - sim.xipos[bid]).max() < 2e-5, name
+        assert np.abs(d["orientation"][e].cpu().numpy() - euler(sim.xmat[bid])).max() < 2e-3, name
+    g = env.get_data("left_ankle_geom")
+    gid = m.name2id(L.OBJ_GEOM, "left_ankle_geom")
+    assert g["type"] == "geom" and np.abs(g["position"][e].cpu().numpy() - sim.geom_xpos[gid]).max() < 2e-5
+    assert np.abs(g["orientation"][e].cpu().numpy() - euler(sim.geom_xmat[gid])).max() < 2e-3
+    assert env.distance("reference", "aux_1").shape == (3,)
+    assert abs(float(env.distance("reference", "aux_1")[e]) - np.linalg.norm(sim.xipos[m.name2id(L.OBJ_BODY, "reference")] - sim.xipos[m.name2id(L.OBJ_BODY, "aux_1")])) < 1e-4
+    xm = env.data.body("aux_1").xmat
+    assert xm.shape == (3, 9) and np.abs(xm[e].cpu().numpy() - sim.xmat[m.name2id(L.OBJ_BODY, "aux_1")]).max() < 1e-4
     with pytest.raises(Exception, match="exportPositions"):
-        env.distance("sender", [n for n in (env.model.id2name(L.OBJ_BODY, i) for i in range(env.model.nbody)) if n and n.startswith("sender") and n != "sender"][0])
+        env.distance("sender", "aux_2")
+    # everything at once
+    env_all = _env(num_envs=2, exportPositions="all")
+    env_all.reset()
+    env_all.step(env_all.sample_actions())
+    assert env_all.distance("aux_4_2", "back_leg").shape == (2,)
