@@ -220,6 +220,9 @@ int mjb_set_env_subset(mjb_batch* b, const int32_t* env_ids_dev, int32_t count);
 int mjb_render(mjb_batch* b, const int32_t* cam_ids, int32_t ncams, int32_t width, int32_t height, uint8_t* rgb_dev);
 /* launch geometry chosen at creation: CTAs, env-warps per CTA, dynamic shared memory per CTA */
 int mjb_batch_geometry(const mjb_batch* b, int32_t* grid, int32_t* warps_per_cta, int64_t* smem_bytes);
+/* debug builds (-DMJB_PHASE_PROF) only: reads and clears the per-phase clock-cycle counters of the step kernel
+ * (step_kernel.cuh PH_*); returns the number of phases, 0 in the product build */
+int mjb_phase_cycles(uint64_t* out, int32_t n);
 /* counter-based draw used for target selection: exported so tests can reproduce the stream */
 uint32_t mjb_draw_u32(uint64_t seed, uint32_t env, uint32_t agent, uint32_t counter);
 

@@ -7,7 +7,8 @@ import struct
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmjb.so")
+# MJB_LIB selects a differently built copy of the same library (debug tooling: the phase-profile build of tools/)
+LIB_PATH = os.environ.get("MJB_LIB") or os.path.join(_HERE, "libmjb.so")
 
 MAX_AGENTS, MAX_PLUGINS, MAX_TARGETS, MAX_EXTRA_PROBES = 8, 4, 16, 48
 SPEC_NO_PACK = 1   # mjb_env_spec.flags
@@ -70,7 +71,7 @@ def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    if build_if_missing:
+    if build_if_missing and not os.environ.get("MJB_LIB"):
         from . import build as _build
         try:
             if _build.needs_build():
@@ -113,6 +114,7 @@ def load(build_if_missing=True):
     lib.mjb_set_env_subset.argtypes = [vp, vp, ctypes.c_int32]
     lib.mjb_render.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp]
     lib.mjb_batch_geometry.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)]
+    lib.mjb_phase_cycles.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
     lib.mjb_draw_u32.restype = ctypes.c_uint32
     lib.mjb_draw_u32.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
     _LIB = lib

@@ -330,6 +330,7 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
     }
     MJB_SYNC();
   }
+  MJB_PH(c, PH_LOAD);
   int ncon = -1;
   // mj_forward (reset / forward modes) is one pass of the same loop body without integration
   const bool integrate = !(mode == MODE_FORWARD || mode == MODE_RESET);
@@ -360,6 +361,7 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
       MJB_SYNC();
     }
   }
+  MJB_PH(c, PH_INTEGRATE);
   if (ncon >= 0 && (B.ncon || B.contact_geom) && K == 1) {
     const uint32_t* pairs = CU(pair_pack);
     if (B.ncon && lane == 0) B.ncon[e0] = ncon;
@@ -441,6 +443,7 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
     probe_slot(i >> 2, k, p1);
     if (writes(k)) B.probe[((size_t)(e0 + k) * dm.np1 + p1) * 4 + (i & 3)] = probe[i];
   }
+  MJB_PH(c, PH_STORE);
   if (mode != MODE_STEP && mode != MODE_RESET) return;
   // ---- epilogue: get_observations (mujoco_parent.py:380-392): sensordata(t) ++ qpos(t+h) ++ qvel(t+h)
   MJB_NOUNROLL
@@ -493,6 +496,7 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
     if (lane < A1 * dm.store_f32) gsf[lane] = s_sf[lane];
     if (lane == 0) B.timestep[env] = *s_ts;
   }
+  MJB_PH(c, PH_EPILOGUE);
 }
 
 }  // namespace mjb

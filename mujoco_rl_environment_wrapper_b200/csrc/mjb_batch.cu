@@ -48,6 +48,10 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
   Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1};
+#if defined(MJB_PHASE_PROF)
+  long long t_last = clock64();
+  c.t_last = &t_last;
+#endif
   // Two scheduling modes share ONE call site of the step code:
   //  * lock-step rounds (default): every env-warp of the CTA takes one env per round and the CTA re-aligns
   //    at each round boundary, so the warps walk through the (large) step code together and share
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
         const int cnt = 32 * (g * gsz + gsz <= warps ? gsz : warps - g * gsz);
         asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "r"(cnt) : "memory");
       } else if (lockstep != 3) __syncthreads();   // mode 3 aligns inside the step (before the collision phase) instead
+      MJB_PH(c, PH_BARRIER);
       env += stride;
     } else {
       __syncwarp();
@@ -601,6 +606,22 @@ int mjb_set_env_subset(mjb_batch* b, const int32_t* env_ids_dev, int32_t count) 
   }
   b->subset = env_ids_dev; b->subset_count = count;
   return MJB_OK;
+}
+
+/* debug build (-DMJB_PHASE_PROF) only: read (and clear) the per-phase cycle counters; returns the number of phases, 0 in
+   the product build */
+int mjb_phase_cycles(uint64_t* out, int32_t n) {
+#if defined(MJB_PHASE_PROF)
+  unsigned long long h[32];
+  if (cudaMemcpyFromSymbol(h, mjb::g_phase_cycles, sizeof(h)) != cudaSuccess) return -1;
+  for (int i = 0; i < n && i < 32; i++) out[i] = h[i];
+  memset(h, 0, sizeof(h));
+  cudaMemcpyToSymbol(mjb::g_phase_cycles, h, sizeof(h));
+  return mjb::PH_COUNT;
+#else
+  (void)out; (void)n;
+  return 0;
+#endif
 }
 
 /* query of the launch geometry, for bench / docs */

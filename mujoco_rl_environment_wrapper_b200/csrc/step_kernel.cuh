@@ -88,7 +88,24 @@ struct Ctx {
   int cta_threads;      // threads of the CTA busy in this lock-step round (0 / 32: no CTA-level alignment)
   int align_all;        // 1: also align around constraints / Newton iterations; 0: only before the collision phase
   float* probe_quat;    // this env's exported orientations in GLOBAL memory (4 floats per probe) or null
+#if defined(MJB_PHASE_PROF)
+  long long* t_last;    // profiling build only: clock of the previous phase mark (lane 0)
+#endif
 };
+// Phase profile (debug build -DMJB_PHASE_PROF, tools/phase_prof.py): lane 0 of every env-warp adds the clock cycles since
+// its previous mark to a global per-phase counter.  Compiled out of the product build.
+enum { PH_LOAD, PH_FK, PH_CRB, PH_RNE, PH_COLLIDE, PH_SENS, PH_CONSTR, PH_NEWTON_INIT, PH_NEWTON_GRAD, PH_NEWTON_HESS, PH_NEWTON_FACTOR,
+       PH_NEWTON_LS, PH_INTEGRATE, PH_STORE, PH_EPILOGUE, PH_BARRIER, PH_ALIGN, PH_COUNT };
+#if defined(MJB_PHASE_PROF) && !defined(MJB_HOST_EMU)
+__device__ unsigned long long g_phase_cycles[32];
+__device__ __forceinline__ void mjb_phase(long long* t_last, int lane, int id) {
+  __syncwarp();
+  if (lane == 0) { long long t = clock64(); atomicAdd(&g_phase_cycles[id], (unsigned long long)(t - *t_last)); *t_last = t; }
+}
+#define MJB_PH(c, id) mjb_phase((c).t_last, (c).lane, (id))
+#else
+#define MJB_PH(c, id) ((void)0)
+#endif
 #define CI(f) ((const int*)(c.img + c.dm->off[IF_##f]))
 #define CU(f) ((const uint32_t*)(c.img + c.dm->off[IF_##f]))
 #define CF(f) ((const float*)(c.img + c.dm->off[IF_##f]))
@@ -1132,6 +1149,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     MJB_SYNC();
   }
   rows_mul(c, ncon, a, jar, aref);
+  MJB_PH(c, PH_NEWTON_INIT);
   int it = 0;
   bool stalled = false, done = false;
   MJB_NOUNROLL
@@ -1171,6 +1189,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     float fn = wsum(lane < nv ? qfrc[lane] * qfrc[lane] + Ma[lane] * Ma[lane] : 0.f);
     if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) done = true;
     }
+    MJB_PH(c, PH_NEWTON_GRAD);
     if (!(c.align_all ? MJB_CTA_ANY(c.cta_threads, !done) : !done)) break;
     if (done) continue;
     it++;
@@ -1220,9 +1239,11 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     MJB_SYNC();
     // factor per tree block unless a contact couples trees (then one block over all dofs)
     const int h0 = coupled ? 0 : t0, h1 = coupled ? (lane < nv ? nv : 0) : t1, hb = coupled ? nv : dm.maxtree;
+    MJB_PH(c, PH_NEWTON_HESS);
     float s = factor_solve(H, H, lane, h0, h1, hb, 0.f, lane < nv ? -g : 0.f, nv);
     if (lane < nv) sv[lane] = s;
     MJB_SYNC();
+    MJB_PH(c, PH_NEWTON_FACTOR);
     rows_mul(c, ncon, sv, jv, nullptr);
     // M s without a matrix product: H s = -g and H = M + J' W J  =>  M s = -g - J' (W (J s)), W = active D
     float mv = 0.f;
@@ -1281,6 +1302,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     MJB_NOUNROLL
     for (int r = lane; r < nrow; r += 32) jar[r] += alpha * jv[r];
     MJB_SYNC();
+    MJB_PH(c, PH_NEWTON_LS);
   }
   return it;
 }
@@ -1437,6 +1459,7 @@ MJB_DEV void sensors_acc(const Ctx& c, int ncon) {
 // =================================================================================================
 // one forward-dynamics evaluation: SF_qpos / qvel / ctrl -> SF_qacc.  Returns the contact count.
 MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out, int* found) {
+  MJB_PH(c, PH_INTEGRATE);
   fk(c);
   if (probes) {
     // exported positions belong to the LAST forward pass of the step (what `data.xipos` holds after
@@ -1463,23 +1486,31 @@ MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out, int
     }
     MJB_SYNC();
   }
+  MJB_PH(c, PH_FK);
   crb_mass(c);
+  MJB_PH(c, PH_CRB);
   rne_pass(c, false);
+  MJB_PH(c, PH_RNE);
   MJB_CTA_SYNC(c.cta_threads);  // re-align the env-warps of the CTA before the data-dependent phases
+  MJB_PH(c, PH_ALIGN);
   int tot[MJB_MAX_PACK] = {0, 0, 0, 0};
   int ncon = collide(c, tot);
+  MJB_PH(c, PH_COLLIDE);
   if (found) {   // contacts found beyond a copy's quota were dropped: keep the count visible (mjb_buffers.ncon_dropped)
 #pragma unroll
     for (int cp = 0; cp < MJB_MAX_PACK; cp++) found[cp] += tot[cp] > c.dm->maxcon1 ? tot[cp] - c.dm->maxcon1 : 0;
   }
   if (sensors) sensors_pos(c);
+  MJB_PH(c, PH_SENS);
   if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
   make_constraints(c, ncon);
+  MJB_PH(c, PH_CONSTR);
   if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
   int it = newton(c, ncon);
   if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
   if (iters_out) *iters_out = it;
   if (sensors) sensors_acc(c, ncon);
+  MJB_PH(c, PH_SENS);
   return ncon;
 }
 
