@@ -52,6 +52,7 @@ namespace mjb {
   X(dof_kind)       /* int [nv]        0 hinge/slide axis in body, 1 free translation, 2 free rotation */ \
   X(dof_t0)         /* int [32]        first dof of the lane's kinematic tree (lane = dof)        */ \
   X(dof_t1)         /* int [32]        one past the last dof of that tree (0 for lanes >= nv)     */ \
+  X(dof_lim)        /* int [32]        limited-joint slot of the dof (lane = dof), -1 = none (also lanes >= nv) */ \
   X(dof_armature)   /* f32 [nv]                                                                  */ \
   X(dof_damping)    /* f32 [nv]                                                                  */ \
   X(geom_type)      /* int [ngeom]                                                               */ \
@@ -109,7 +110,7 @@ enum ImageField {
   X(con)                                  /* contacts: dist, pos3, frame9, pair, mu, pad -> 16   */ \
   X(J)                                    /* contact Jacobians, 3 rows per contact (n, t1, t2)   */ \
   X(efcD) X(efcAref) X(efcJar) X(efcJv)   /* per-row: limits 2*nlim then 4 per contact           */ \
-  X(vecA) X(vecB) X(vecC) X(vecD)         /* nv-sized temporaries (Ma, grad, search, Mv)         */ \
+  X(vecA) X(vecB) X(vecC) X(vecD)         /* nv-sized temporaries (force, grad, search, spare)    */ \
   X(rk)                                   /* RK4 stage storage: q0, v0, dq, dv                    */ \
   X(sens)                                 /* sensordata                                          */
 

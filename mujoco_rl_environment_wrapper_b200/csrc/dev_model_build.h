@@ -210,6 +210,12 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
     w.begin(IF_dof_t0); for (int v : t0) w.i(v);
     w.begin(IF_dof_t1); for (int v : t1) w.i(v);
   }
+  {
+    int dl[32];
+    for (int d = 0; d < 32; d++) dl[d] = -1;
+    for (size_t k = 0; k < lim.size(); k++) { int d = m.jnt_dofadr[lim[k]]; if (d >= 0 && d < 32) dl[d] = (int)k; }
+    w.begin(IF_dof_lim); for (int v : dl) w.i(v);
+  }
   w.begin(IF_dof_armature); for (int d = 0; d < m.nv; d++) w.f(m.dof_armature[d]);
   w.begin(IF_dof_damping);
   for (int d = 0; d < m.nv; d++) { w.f(m.dof_damping[d]); if (m.dof_damping[d] > 0) dm.has_damping = 1; }

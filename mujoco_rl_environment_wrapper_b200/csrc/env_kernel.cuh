@@ -488,9 +488,16 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
       if (lane == 0) *s_ts = B.timestep[env];
     }
     MJB_SYNC();
-    if (lane == 0)
-      run_plugins<MJB_MAX_AGENTS>(dm, SF(ctrl) + k * dm.nu1, B.obs + (size_t)env * A1 * dm.obs_stride, B.reward + (size_t)env * A1, B.term + (size_t)env * (A1 + 1),
-                  B.trunc + (size_t)env * (A1 + 1), env, k, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
+    if (lane == 0) {
+      // up to two agents (every level of the reference): the per-agent accumulators of the programme live in registers
+      if (MJB_LIKELY(A1 <= 2))
+        run_plugins<2>(dm, SF(ctrl) + k * dm.nu1, B.obs + (size_t)env * A1 * dm.obs_stride, B.reward + (size_t)env * A1, B.term + (size_t)env * (A1 + 1),
+                       B.trunc + (size_t)env * (A1 + 1), env, k, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
+      else
+        run_plugins<MJB_MAX_AGENTS>(dm, SF(ctrl) + k * dm.nu1, B.obs + (size_t)env * A1 * dm.obs_stride, B.reward + (size_t)env * A1,
+                                    B.term + (size_t)env * (A1 + 1), B.trunc + (size_t)env * (A1 + 1), env, k, mode == MODE_RESET, probe, s_si, s_sf,
+                                    s_act, s_ts);
+    }
     MJB_SYNC();
     for (int i = lane; i < A1 * dm.store_i32; i += 32) gsi[i] = s_si[i];
     if (lane < A1 * dm.store_f32) gsf[lane] = s_sf[lane];

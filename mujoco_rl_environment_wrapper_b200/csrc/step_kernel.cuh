@@ -95,7 +95,7 @@ struct Ctx {
 // Phase profile (debug build -DMJB_PHASE_PROF, tools/phase_prof.py): lane 0 of every env-warp adds the clock cycles since
 // its previous mark to a global per-phase counter.  Compiled out of the product build.
 enum { PH_LOAD, PH_FK, PH_CRB, PH_RNE, PH_COLLIDE, PH_SENS, PH_CONSTR, PH_NEWTON_INIT, PH_NEWTON_GRAD, PH_NEWTON_HESS, PH_NEWTON_FACTOR,
-       PH_NEWTON_LS, PH_INTEGRATE, PH_STORE, PH_EPILOGUE, PH_BARRIER, PH_ALIGN, PH_COUNT };
+       PH_NEWTON_LS, PH_INTEGRATE, PH_STORE, PH_EPILOGUE, PH_BARRIER, PH_ALIGN, PH_LS_ROWSMUL, PH_LS_MV, PH_LS_LOOP, PH_COUNT };
 #if defined(MJB_PHASE_PROF) && !defined(MJB_HOST_EMU)
 __device__ unsigned long long g_phase_cycles[32];
 __device__ __forceinline__ void mjb_phase(long long* t_last, int lane, int id) {
@@ -103,8 +103,10 @@ __device__ __forceinline__ void mjb_phase(long long* t_last, int lane, int id) {
   if (lane == 0) { long long t = clock64(); atomicAdd(&g_phase_cycles[id], (unsigned long long)(t - *t_last)); *t_last = t; }
 }
 #define MJB_PH(c, id) mjb_phase((c).t_last, (c).lane, (id))
+#define MJB_COUNT(c, slot, n) do { if ((c).lane == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(n)); } while (0)
 #else
 #define MJB_PH(c, id) ((void)0)
+#define MJB_COUNT(c, slot, n) ((void)0)
 #endif
 #define CI(f) ((const int*)(c.img + c.dm->off[IF_##f]))
 #define CU(f) ((const uint32_t*)(c.img + c.dm->off[IF_##f]))
@@ -1129,65 +1131,93 @@ MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const 
   MJB_SYNC();
 }
 
-// primal Newton solve for qacc (SF_qacc holds the warm start on entry, the solution on exit).
-// On exit SF_vecA = M qacc, SF_vecB = gradient, SF_efcJar = J qacc - aref.  Returns iterations used.
+// J' w for a per-row weight vector w (limit rows +-e_dof, contact rows = pyramid edges): the lane's dof component
+MJB_DEV float jt_mul(const Ctx& c, int ncon, int base, int mylim, const float* w) {
+  const DevModel& dm = *c.dm;
+  const float* J = SF(J);
+  const float* con = SF(con);
+  float out = mylim >= 0 ? w[2 * mylim] - w[2 * mylim + 1] : 0.f;
+  MJB_NOUNROLL
+  for (int k = 0; k < ncon; k++) {
+    const uint32_t mask = ((const uint32_t*)(con + CON_STRIDE * k))[CON_MASK];
+    if (!((mask >> c.lane) & 1u)) continue;
+    const float mu = con[CON_STRIDE * k + CON_MU];
+    const float w0 = w[base + 4 * k], w1 = w[base + 4 * k + 1], w2 = w[base + 4 * k + 2], w3 = w[base + 4 * k + 3];
+    const int idx = MJB_POPC(mask & ((1u << c.lane) - 1u));
+    out += J[(3 * k) * dm.ldj + idx] * ((w0 + w1) + (w2 + w3)) + J[(3 * k + 1) * dm.ldj + idx] * (mu * (w0 - w1)) +
+           J[(3 * k + 2) * dm.ldj + idx] * (mu * (w2 - w3));
+  }
+  return out;
+}
+// the same for two weight vectors at once (one pass over the Jacobian)
+MJB_DEV void jt_mul2(const Ctx& c, int ncon, int base, int mylim, const float* w, const float* v, float& ow, float& ov) {
+  const DevModel& dm = *c.dm;
+  const float* J = SF(J);
+  const float* con = SF(con);
+  ow = mylim >= 0 ? w[2 * mylim] - w[2 * mylim + 1] : 0.f;
+  ov = mylim >= 0 ? v[2 * mylim] - v[2 * mylim + 1] : 0.f;
+  MJB_NOUNROLL
+  for (int k = 0; k < ncon; k++) {
+    const uint32_t mask = ((const uint32_t*)(con + CON_STRIDE * k))[CON_MASK];
+    if (!((mask >> c.lane) & 1u)) continue;
+    const float mu = con[CON_STRIDE * k + CON_MU];
+    const float w0 = w[base + 4 * k], w1 = w[base + 4 * k + 1], w2 = w[base + 4 * k + 2], w3 = w[base + 4 * k + 3];
+    const float v0 = v[base + 4 * k], v1 = v[base + 4 * k + 1], v2 = v[base + 4 * k + 2], v3 = v[base + 4 * k + 3];
+    const int idx = MJB_POPC(mask & ((1u << c.lane) - 1u));
+    const float jn = J[(3 * k) * dm.ldj + idx], j1 = J[(3 * k + 1) * dm.ldj + idx], j2 = J[(3 * k + 2) * dm.ldj + idx];
+    ow += jn * ((w0 + w1) + (w2 + w3)) + j1 * (mu * (w0 - w1)) + j2 * (mu * (w2 - w3));
+    ov += jn * ((v0 + v1) + (v2 + v3)) + j1 * (mu * (v0 - v1)) + j2 * (mu * (v2 - v3));
+  }
+}
+
+// primal Newton solve for qacc.  The cost is s(a) = 1/2 (a - a0)' M (a - a0) + 1/2 sum_r D_r min(x_r, 0)^2 with
+// x = J a - aref (a0 = M^-1 qfrc_smooth), its gradient g = M a - qfrc_smooth - J' f, f_r = -D_r min(x_r, 0).
+// M a is never formed: the iteration starts at a0 (g = -J' f), and after a step a+ = a + alpha s along the Newton
+// direction of the current active set (H s = -g, H = M + J' W J) the gradient follows from the rows that SWITCHED
+// between active and inactive alone:      g+ = (1 - alpha) g - J' u,   u_r = D_r |x_r+| on switched rows, else 0
+// (every other row's change of force is cancelled exactly by the W J s term of M s = -g - J' W J s).  A step in which
+// no row switches and alpha = 1 therefore ends with g = 0: the solve terminates on the exact active set.
+// On exit SF_qacc = solution, SF_vecA = qfrc_smooth + J' f (= M a - g: the total force the implicit-damping solve
+// needs), SF_vecB = g, SF_efcJar = J a - aref.  Returns iterations used.
 MJB_DEV int newton(const Ctx& c, int ncon) {
   const DevModel& dm = *c.dm;
   const int nv = dm.nv, lane = c.lane;
   const int t0 = CI(dof_t0)[lane], t1 = CI(dof_t1)[lane];
-  float *M = SF(M), *H = SF(H), *a = SF(qacc), *qfrc = SF(qfrc), *Ma = SF(vecA), *grad = SF(vecB), *sv = SF(vecC), *Mv = SF(vecD);
-  float *D = SF(efcD), *aref = SF(efcAref), *jar = SF(efcJar), *jv = SF(efcJv);
+  float *M = SF(M), *H = SF(H), *a = SF(qacc), *sv = SF(vecC);
+  float *D = SF(efcD), *frc = SF(efcAref), *jar = SF(efcJar), *jv = SF(efcJv);   // frc overwrites aref once jar is formed
   const float* J = SF(J);
   const float* con = SF(con);
   const uint32_t* pairs = CU(pair_pack);
   const int base = 2 * dm.nlim, nrow = base + 4 * ncon;
-  // start from the unconstrained acceleration a0 = M^-1 qfrc_smooth (fewer Newton iterations than the
-  // previous step's qacc under fast-changing controls, and exact when no constraint row is active)
+  float *qfrc = SF(qfrc), *tot = SF(vecA);   // tot = qfrc_smooth + J' f of the current iterate
+  // start from the unconstrained acceleration a0 = M^-1 qfrc_smooth (fewer Newton iterations than the previous step's
+  // qacc under fast-changing controls, and exact when no constraint row is active)
   {
     float x = factor_solve(M, H, lane, t0, t1, dm.maxtree, 0.f, lane < nv ? qfrc[lane] : 0.f, nv);
-    if (lane < nv) { a[lane] = x; Ma[lane] = qfrc[lane]; }
+    if (lane < nv) a[lane] = x;
     MJB_SYNC();
   }
-  rows_mul(c, ncon, a, jar, aref);
+  rows_mul(c, ncon, a, jar, frc);
+  MJB_NOUNROLL
+  for (int r = lane; r < nrow; r += 32) { const float x = jar[r]; frc[r] = x < 0.f ? -D[r] * x : 0.f; }
+  MJB_SYNC();
+  float g = 0.f;
+  if (lane < nv) {
+    const float q = jt_mul(c, ncon, base, CI(dof_lim)[lane], frc);   // J' f
+    g = -q;
+    tot[lane] = qfrc[lane] + q;
+  }
   MJB_PH(c, PH_NEWTON_INIT);
   int it = 0;
   bool stalled = false, done = false;
   MJB_NOUNROLL
   for (;;) {
-    // Iterations are aligned across the env-warps of the CTA (they then share instruction-cache lines); a
-    // warp whose env has converged idles at the barrier until every env of the round is done.
-    float g = 0.f;
+    // Iterations can be aligned across the env-warps of the CTA (c.align_all: they then share instruction-cache
+    // lines); a warp whose env has converged idles at the barrier until every env of the round is done.
     if (!done) {
-    // gradient = M a - qfrc_smooth - J' f
-    if (lane < nv) {
-      g = Ma[lane] - qfrc[lane];
-      MJB_NOUNROLL
-      for (int k = 0; k < ncon; k++) {
-        float mu = con[CON_STRIDE * k + CON_MU];
-        float f0 = jar[base + 4 * k] < 0 ? -D[base + 4 * k] * jar[base + 4 * k] : 0.f;
-        float f1 = jar[base + 4 * k + 1] < 0 ? -D[base + 4 * k + 1] * jar[base + 4 * k + 1] : 0.f;
-        float f2 = jar[base + 4 * k + 2] < 0 ? -D[base + 4 * k + 2] * jar[base + 4 * k + 2] : 0.f;
-        float f3_ = jar[base + 4 * k + 3] < 0 ? -D[base + 4 * k + 3] * jar[base + 4 * k + 3] : 0.f;
-        uint32_t mask = ((const uint32_t*)(con + CON_STRIDE * k))[CON_MASK];
-        if ((mask >> lane) & 1u) {
-          int idx = MJB_POPC(mask & ((1u << lane) - 1u));
-          g -= J[(3 * k) * dm.ldj + idx] * (f0 + f1 + f2 + f3_) + J[(3 * k + 1) * dm.ldj + idx] * mu * (f0 - f1) +
-               J[(3 * k + 2) * dm.ldj + idx] * mu * (f2 - f3_);
-        }
-      }
-      grad[lane] = g;
-    }
-    MJB_SYNC();
-    MJB_NOUNROLL
-    for (int k = lane; k < dm.nlim; k += 32) {
-      float flo = jar[2 * k] < 0 ? -D[2 * k] * jar[2 * k] : 0.f, fhi = jar[2 * k + 1] < 0 ? -D[2 * k + 1] * jar[2 * k + 1] : 0.f;
-      grad[CI(lim_dof)[k]] -= flo - fhi;
-    }
-    MJB_SYNC();
-    g = lane < nv ? grad[lane] : 0.f;
-    float gn = wsum(g * g);
-    float fn = wsum(lane < nv ? qfrc[lane] * qfrc[lane] + Ma[lane] * Ma[lane] : 0.f);
-    if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) done = true;
+      const float qf = lane < nv ? qfrc[lane] : 0.f, ma = lane < nv ? tot[lane] + g : 0.f;   // M a = qfrc_smooth + J' f + g
+      const float gn = wsum(g * g), fn = wsum(qf * qf + ma * ma);
+      if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) done = true;
     }
     MJB_PH(c, PH_NEWTON_GRAD);
     if (!(c.align_all ? MJB_CTA_ANY(c.cta_threads, !done) : !done)) break;
@@ -1203,10 +1233,9 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       for (int i = lane; i < ((nv * (nv + 1)) / 2 + 3) / 4; i += 32) dst[i] = src[i];
     }
     MJB_SYNC();
-    MJB_NOUNROLL
-    for (int k = lane; k < dm.nlim; k += 32) {
-      int d = CI(lim_dof)[k];
-      H[tri(d, d)] += (jar[2 * k] < 0 ? D[2 * k] : 0.f) + (jar[2 * k + 1] < 0 ? D[2 * k + 1] : 0.f);
+    {
+      const int mylim = CI(dof_lim)[lane];
+      if (mylim >= 0) H[tri(lane, lane)] += (jar[2 * mylim] < 0 ? D[2 * mylim] : 0.f) + (jar[2 * mylim + 1] < 0 ? D[2 * mylim + 1] : 0.f);
     }
     MJB_SYNC();
     bool coupled = false;  // does an active contact couple two kinematic trees?
@@ -1240,44 +1269,29 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     // factor per tree block unless a contact couples trees (then one block over all dofs)
     const int h0 = coupled ? 0 : t0, h1 = coupled ? (lane < nv ? nv : 0) : t1, hb = coupled ? nv : dm.maxtree;
     MJB_PH(c, PH_NEWTON_HESS);
-    float s = factor_solve(H, H, lane, h0, h1, hb, 0.f, lane < nv ? -g : 0.f, nv);
-    if (lane < nv) sv[lane] = s;
+    float s = factor_solve(H, H, lane, h0, h1, hb, 0.f, -g, nv);
+    if (lane < nv) sv[lane] = s; else s = 0.f;
     MJB_SYNC();
     MJB_PH(c, PH_NEWTON_FACTOR);
     rows_mul(c, ncon, sv, jv, nullptr);
-    // M s without a matrix product: H s = -g and H = M + J' W J  =>  M s = -g - J' (W (J s)), W = active D
-    float mv = 0.f;
-    if (lane < nv) {
-      mv = -g;
-      MJB_NOUNROLL
-      for (int k = 0; k < ncon; k++) {
-        uint32_t mask = ((const uint32_t*)(con + CON_STRIDE * k))[CON_MASK];
-        if (!((mask >> lane) & 1u)) continue;
-        float mu = con[CON_STRIDE * k + CON_MU];
-        float u0 = jar[base + 4 * k] < 0 ? D[base + 4 * k] * jv[base + 4 * k] : 0.f;
-        float u1 = jar[base + 4 * k + 1] < 0 ? D[base + 4 * k + 1] * jv[base + 4 * k + 1] : 0.f;
-        float u2 = jar[base + 4 * k + 2] < 0 ? D[base + 4 * k + 2] * jv[base + 4 * k + 2] : 0.f;
-        float u3 = jar[base + 4 * k + 3] < 0 ? D[base + 4 * k + 3] * jv[base + 4 * k + 3] : 0.f;
-        int idx = MJB_POPC(mask & ((1u << lane) - 1u));
-        mv -= J[(3 * k) * dm.ldj + idx] * (u0 + u1 + u2 + u3) + J[(3 * k + 1) * dm.ldj + idx] * mu * (u0 - u1) +
-              J[(3 * k + 2) * dm.ldj + idx] * mu * (u2 - u3);
-      }
-      Mv[lane] = mv;
-    }
-    MJB_SYNC();
+    MJB_PH(c, PH_LS_ROWSMUL);
+    // slope and curvature of the smooth part along s without M:  s'(M a - qfrc) = g's + f'Js,  s'M s = -g's - (Js)'W(Js)
+    float a1 = 0.f, a2 = 0.f;
     MJB_NOUNROLL
-    for (int k = lane; k < dm.nlim; k += 32) {
-      float ulo = jar[2 * k] < 0 ? D[2 * k] * jv[2 * k] : 0.f, uhi = jar[2 * k + 1] < 0 ? D[2 * k + 1] * jv[2 * k + 1] : 0.f;
-      Mv[CI(lim_dof)[k]] -= ulo - uhi;
+    for (int r = lane; r < nrow; r += 32) {
+      const float v = jv[r];
+      a1 += frc[r] * v;
+      if (jar[r] < 0.f) a2 += D[r] * v * v;
     }
-    MJB_SYNC();
-    mv = lane < nv ? Mv[lane] : 0.f;
-    float p1 = wsum(lane < nv ? s * (Ma[lane] - qfrc[lane]) : 0.f);
-    float p2 = wsum(lane < nv ? s * mv : 0.f);
-    // exact line search on the convex piecewise-quadratic phi(alpha): safeguarded Newton on phi'
-    float alpha = 0.f, lo = 0.f, hi = MJB_BIG, d1_0 = 0.f;
+    const float d1_0 = wsum(g * s);   // phi'(0)
+    const float p1 = d1_0 + wsum(a1), p2 = -d1_0 - wsum(a2);
+    MJB_PH(c, PH_LS_MV);
+    // exact line search on the convex piecewise-quadratic phi(alpha): safeguarded Newton on phi'.  s is the exact Newton
+    // direction of the current active set, so the first trial is alpha = 1 (the minimiser whenever no row switches
+    // along the step: then one evaluation ends the search)
+    float alpha = 1.f, lo = 0.f, hi = MJB_BIG;
     MJB_NOUNROLL
-    for (int ls = 0; ls <= dm.ls_iterations; ls++) {
+    for (int ls = 1; ls <= dm.ls_iterations; ls++) {
       float d1 = 0.f, d2 = 0.f;
       MJB_NOUNROLL
       for (int r = lane; r < nrow; r += 32) {
@@ -1286,24 +1300,38 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       }
       d1 = wsum(d1) + p1 + alpha * p2;
       d2 = wsum(d2) + p2;
-      if (ls == 0) d1_0 = d1;
-      else {
-        if (fabsf(d1) <= 1e-6f * fabsf(d1_0)) break;
-        if (d1 < 0.f) lo = alpha; else hi = alpha;
-      }
+      MJB_COUNT(c, 24, 1);   // line-search evaluations
+      if (fabsf(d1) <= 1e-6f * fabsf(d1_0)) break;
+      if (d1 < 0.f) lo = alpha; else hi = alpha;
       if (ls == dm.ls_iterations) break;
       float nxt = alpha - d1 / fmaxf(d2, MJB_MINVAL);
-      if (!(nxt > lo && nxt < hi)) nxt = hi < MJB_BIG ? 0.5f * (lo + hi) : (alpha > 0.f ? 2.f * alpha : 1.f);
+      if (!(nxt > lo && nxt < hi)) nxt = hi < MJB_BIG ? 0.5f * (lo + hi) : 2.f * alpha;
       alpha = nxt;
     }
+    MJB_COUNT(c, 25, 1);     // Newton iterations
+    MJB_PH(c, PH_LS_LOOP);
     float amax = wmax(lane < nv ? fabsf(a[lane]) : 0.f), smax = wmax(fabsf(alpha * s));
     stalled = smax <= 1e-7f * (1.f + amax);
-    if (lane < nv) { a[lane] += alpha * s; Ma[lane] += alpha * mv; }
+    if (lane < nv) a[lane] += alpha * s;
+    // rows: new residual, new force, and the switched rows' term of the gradient update (kept in jv)
     MJB_NOUNROLL
-    for (int r = lane; r < nrow; r += 32) jar[r] += alpha * jv[r];
+    for (int r = lane; r < nrow; r += 32) {
+      const float xo = jar[r], xn = xo + alpha * jv[r], d = D[r];
+      jar[r] = xn;
+      frc[r] = xn < 0.f ? -d * xn : 0.f;
+      jv[r] = ((xo < 0.f) != (xn < 0.f)) ? d * fabsf(xn) : 0.f;
+    }
     MJB_SYNC();
+    if (lane < nv) {
+      float gu, q;
+      jt_mul2(c, ncon, base, CI(dof_lim)[lane], jv, frc, gu, q);
+      g = (1.f - alpha) * g - gu;
+      tot[lane] = qfrc[lane] + q;
+    }
     MJB_PH(c, PH_NEWTON_LS);
   }
+  if (lane < nv) SF(vecB)[lane] = g;
+  MJB_SYNC();
   return it;
 }
 
@@ -1588,10 +1616,10 @@ MJB_DEV int substep(const Ctx& c, bool sensors, bool integrate, int* iters_out, 
   }
   float acc = lane < nv ? qacc[lane] : 0.f;
   if (dm.has_damping) {
-    // (M + h D) a' = qfrc_smooth + qfrc_constraint  ( = M a - gradient at the solver's exit point)
+    // (M + h D) a' = qfrc_smooth + qfrc_constraint
     float *M = SF(M), *H = SF(H);
     const int t0 = CI(dof_t0)[lane], t1 = CI(dof_t1)[lane];
-    float rhs = lane < nv ? SF(vecA)[lane] - SF(vecB)[lane] : 0.f;
+    float rhs = lane < nv ? SF(vecA)[lane] : 0.f;   // qfrc_smooth + J' f at the solver's exit point
     MJB_SYNC();
     acc = factor_solve(M, H, lane, t0, t1, dm.maxtree, lane < nv ? h * CF(dof_damping)[lane] : 0.f, rhs, nv);
   }

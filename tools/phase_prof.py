@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "mujoco_rl_environment_wrapper_b200")
 PROF_LIB = os.path.join(PKG, "libmjb_prof.so")
 PHASES = ["load", "fk", "crb", "rne", "collide", "sensors", "constraints", "newton_init", "newton_grad", "newton_hess", "newton_factor",
-          "newton_linesearch", "integrate", "store", "epilogue", "round_barrier", "align"]
+          "newton_linesearch", "integrate", "store", "epilogue", "round_barrier", "align", "ls_rowsmul", "ls_Mv", "ls_loop"]
 
 
 def build():
@@ -52,7 +52,8 @@ def main():
         nph = lib.mjb_phase_cycles(buf, 32)
         tot = sum(buf[i] for i in range(nph))
         rec = {"envs": n, "cycles_per_env_step": tot / (n * steps), "niter_mean": float(b.niter.float().mean()), "ncon_mean": float(b.ncon.float().mean()),
-               "phases": {PHASES[i]: round(buf[i] / tot, 4) for i in range(nph)}}
+               "phases": {PHASES[i]: round(buf[i] / tot, 4) for i in range(nph)},
+               "linesearch_evals_per_newton_iter": buf[24] / max(1, buf[25]), "newton_iters_per_env_step": buf[25] / (n * steps)}
         print(json.dumps(rec), flush=True)
         out.append(rec)
         del env, b
