@@ -513,7 +513,9 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
   sizes[SF_M] = tri; sizes[SF_H] = tri;
   sizes[SF_cand] = dm.maxcand;
   sizes[SF_con] = CON_STRIDE * dm.maxcon;
-  sizes[SF_J] = std::max(3 * dm.maxcon * dm.ldj, MJB_MAX_AGENTS * (MJB_STORE_I_COUNT + MJB_STORE_F_COUNT) + 64 + 4);
+  // (the epilogue re-uses J: plugin store rows, actions, step counter, then the fp64 agent - target distance table)
+  const int plug_words = MJB_MAX_AGENTS * (MJB_STORE_I_COUNT + MJB_STORE_F_COUNT) + 64 + 4 + 2 * std::max(1, spec.n_agents * std::max(1, spec.n_targets));
+  sizes[SF_J] = std::max(3 * dm.maxcon * dm.ldj, plug_words);
   if (spec.n_agents * MJB_STORE_I_COUNT > 64 || spec.n_agents * r4(std::max(1, spec.act_dim)) > 64 || spec.n_agents * MJB_STORE_F_COUNT > 32)
     throw std::runtime_error("kernel limit: per-env plugin rows exceed the epilogue staging area");
   sizes[SF_efcD] = sizes[SF_efcAref] = sizes[SF_efcJar] = sizes[SF_efcJv] = dm.maxefc;
@@ -525,7 +527,7 @@ inline void build_dev_model(const ModelView& m, const mjb_env_spec& spec, DevIma
     // needs its state rows and the epilogue staging area -> many more envs in flight per SM
     for (int i = 0; i < SF_COUNT; i++)
       if (i != SF_qpos && i != SF_qvel && i != SF_qacc && i != SF_ctrl && i != SF_qfrc && i != SF_sens && i != SF_J) sizes[i] = 0;
-    sizes[SF_J] = MJB_MAX_AGENTS * (MJB_STORE_I_COUNT + MJB_STORE_F_COUNT) + 64 + 4;
+    sizes[SF_J] = plug_words;
   }
   // lifetime aliasing: the Hessian lives where cinert + crb were (dead once the bias forces are known),
   // the broad-phase candidate list where cvel + cacc are (dead between the bias pass and the sensors)

@@ -61,9 +61,11 @@ MJB_DEV void st_dist(float* sfa, double d) {
 // live in registers and the loops unroll; MJB_MAX_AGENTS is the general form.
 template <int AMAX>
 MJB_DEV void run_plugins(const DevModel& dm, const float* ctrl, float* obs, float* rew, uint8_t* term, uint8_t* trunc, int env, int copy,
-                         bool is_reset, const float* probe, int* si, float* sf, const float* act, int* ts_io) {
+                         bool is_reset, const float* probe, int* si, float* sf, const float* act, int* ts_io, const double* dtab = nullptr) {
   // `env` is the REAL environment, `copy` its slot inside the (possibly packed) virtual env of this warp
   const int A = dm.a1, ab = copy * dm.a1, tb = copy * dm.t1, n_targets = dm.t1;
+  // agent - target distance: from the table the warp filled lane-parallel (dist_table), or evaluated here
+  auto pdist = [&](int a, int t) { return dtab ? dtab[a * n_targets + t] : probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + t]); };
   double reward[AMAX];
   bool done[AMAX];
   int opos[AMAX];
@@ -99,13 +101,13 @@ MJB_DEV void run_plugins(const DevModel& dm, const float* ctrl, float* obs, floa
           sia[MJB_STORE_I_TARGET] = tgt;
         }
         if (tgt > 0) {
-          const double d = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
+          const double d = pdist(a, tgt - 1);
           if (d < (double)dyn.param[0]) {
             sia[MJB_STORE_I_INVENTORY] ^= 1;
             reward[a] += 1.0;
             tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)n_targets);
             sia[MJB_STORE_I_TARGET] = tgt;
-            st_dist(sfa, probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]));
+            st_dist(sfa, pdist(a, tgt - 1));
           }
           const float* tp = probe + 4 * dm.target_probe[tb + tgt - 1];
           oa[opos[a]] = tp[0]; oa[opos[a] + 1] = tp[1]; oa[opos[a] + 2] = tp[2];
@@ -144,9 +146,9 @@ MJB_DEV void run_plugins(const DevModel& dm, const float* ctrl, float* obs, floa
         if (tgt == 0) {
           tgt = 1 + (int)(draw_u32(dm.seed, env, a, sia[MJB_STORE_I_DRAWS]++) % (uint32_t)n_targets);
           sia[MJB_STORE_I_TARGET] = tgt;
-          st_dist(sfa, probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]));
+          st_dist(sfa, pdist(a, tgt - 1));
         } else {
-          const double d = probe_dist(probe, dm.agent_probe[ab + a], dm.target_probe[tb + tgt - 1]);
+          const double d = pdist(a, tgt - 1);
           reward[a] += (ld_dist(sfa) - d) * (double)rf.param[0];
           st_dist(sfa, d);
         }
@@ -459,12 +461,14 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
       oa[i] = kind == 0 ? sens[adr] : (kind == 1 ? qpos[adr] : qvel[adr]);
     }
   }
+  MJB_PH(c, PH_EPI_OBS);
   // plugins per real env: its store rows, dynamic actions and step counter are staged in shared memory (the
   // contact Jacobian scratch is dead by now) so that one lane can run the reference-order programme on them
   int* s_si = (int*)SF(J);
   float* s_sf = SF(J) + MJB_MAX_AGENTS * MJB_STORE_I_COUNT;
   float* s_act = s_sf + MJB_MAX_AGENTS * MJB_STORE_F_COUNT;
   int* s_ts = (int*)(s_act + 64);
+  double* s_dtab = (double*)(s_ts + 4);   // [a1, t1] agent - target distances of the copy being processed
   MJB_NOUNROLL
   for (int k = 0; k < K; k++) {
     if (!writes(k)) continue;
@@ -487,18 +491,26 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
       if (lane < A1 * dm.store_f32) s_sf[lane] = gsf[lane];
       if (lane == 0) *s_ts = B.timestep[env];
     }
+    // every agent - target distance of this env, one pair per lane (fp64: run_plugins then only looks them up)
+    MJB_NOUNROLL
+    for (int i = lane; i < A1 * dm.t1; i += 32) {
+      const int a = i / dm.t1, t = i - a * dm.t1;
+      s_dtab[i] = probe_dist(probe, dm.agent_probe[k * A1 + a], dm.target_probe[k * dm.t1 + t]);
+    }
     MJB_SYNC();
+    MJB_PH(c, PH_EPI_STAGE);
     if (lane == 0) {
       // up to two agents (every level of the reference): the per-agent accumulators of the programme live in registers
       if (MJB_LIKELY(A1 <= 2))
         run_plugins<2>(dm, SF(ctrl) + k * dm.nu1, B.obs + (size_t)env * A1 * dm.obs_stride, B.reward + (size_t)env * A1, B.term + (size_t)env * (A1 + 1),
-                       B.trunc + (size_t)env * (A1 + 1), env, k, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts);
+                       B.trunc + (size_t)env * (A1 + 1), env, k, mode == MODE_RESET, probe, s_si, s_sf, s_act, s_ts, s_dtab);
       else
         run_plugins<MJB_MAX_AGENTS>(dm, SF(ctrl) + k * dm.nu1, B.obs + (size_t)env * A1 * dm.obs_stride, B.reward + (size_t)env * A1,
                                     B.term + (size_t)env * (A1 + 1), B.trunc + (size_t)env * (A1 + 1), env, k, mode == MODE_RESET, probe, s_si, s_sf,
-                                    s_act, s_ts);
+                                    s_act, s_ts, s_dtab);
     }
     MJB_SYNC();
+    MJB_PH(c, PH_EPI_PLUG);
     for (int i = lane; i < A1 * dm.store_i32; i += 32) gsi[i] = s_si[i];
     if (lane < A1 * dm.store_f32) gsf[lane] = s_sf[lane];
     if (lane == 0) B.timestep[env] = *s_ts;

@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
   mbar_wait(bar, 0);
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
-  Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1};
+  // MJB_LOCKSTEP: 2 rounds only, 1 rounds + every alignment point, 3 rounds replaced by a sync before the collision phase,
+  // 4 (default) rounds + re-alignment after the Newton solve, 5 = 4 + before the collision phase
+  Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1 ? 7 : (lockstep == 3 ? 2 : (lockstep == 4 ? 4 : (lockstep == 5 ? 6 : 0)))};
 #if defined(MJB_PHASE_PROF)
   long long t_last = clock64();
   c.t_last = &t_last;
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
   int env = blockIdx.x * warps + warp;
   for (int r = 0;; r++) {
     if (lockstep ? (r >= rounds) : (env >= nvirt)) break;
-    if (lockstep == 1 || lockstep == 3) {
+    if (lockstep != 0 && lockstep != 2) {
       int busy = nvirt - (blockIdx.x * warps + r * stride);  // env-warps of this CTA with work in this round
       // (a masked reset lets warps skip their env, so intra-step alignment is off for it)
       c.cta_threads = (mask == nullptr ? 32 : 0) * (busy > warps ? warps : (busy < 0 ? 0 : busy));
@@ -350,7 +352,7 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     mjb::set_error("mjb_batch_create: stream / event creation failed");
     return fail(MJB_ERR_CUDA);
   }
-  b->lockstep = mjb::env_int("MJB_LOCKSTEP", 2);
+  b->lockstep = mjb::env_int("MJB_LOCKSTEP", 4);
   b->groups = mjb::env_int("MJB_GROUPS", 1);
   if (b->groups < 1 || b->groups > 8 || b->lockstep != 2) b->groups = 1;
   const int A = dm.a1;

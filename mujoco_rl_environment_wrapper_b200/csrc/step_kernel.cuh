@@ -86,7 +86,8 @@ struct Ctx {
   int lane;
   float* probe;         // exported positions of this env (shared memory, 4 floats per probe)
   int cta_threads;      // threads of the CTA busy in this lock-step round (0 / 32: no CTA-level alignment)
-  int align_all;        // 1: also align around constraints / Newton iterations; 0: only before the collision phase
+  int align_all;        // CTA-level re-alignment points inside the step (bits): 1 constraints / Newton iterations, 2 before the
+                        // collision phase, 4 after the Newton solve (the data-dependent part): see k_env
   float* probe_quat;    // this env's exported orientations in GLOBAL memory (4 floats per probe) or null
 #if defined(MJB_PHASE_PROF)
   long long* t_last;    // profiling build only: clock of the previous phase mark (lane 0)
@@ -95,7 +96,7 @@ struct Ctx {
 // Phase profile (debug build -DMJB_PHASE_PROF, tools/phase_prof.py): lane 0 of every env-warp adds the clock cycles since
 // its previous mark to a global per-phase counter.  Compiled out of the product build.
 enum { PH_LOAD, PH_FK, PH_CRB, PH_RNE, PH_COLLIDE, PH_SENS, PH_CONSTR, PH_NEWTON_INIT, PH_NEWTON_GRAD, PH_NEWTON_HESS, PH_NEWTON_FACTOR,
-       PH_NEWTON_LS, PH_INTEGRATE, PH_STORE, PH_EPILOGUE, PH_BARRIER, PH_ALIGN, PH_LS_ROWSMUL, PH_LS_MV, PH_LS_LOOP, PH_COUNT };
+       PH_NEWTON_LS, PH_INTEGRATE, PH_STORE, PH_EPILOGUE, PH_BARRIER, PH_ALIGN, PH_LS_ROWSMUL, PH_LS_MV, PH_LS_LOOP, PH_EPI_OBS, PH_EPI_STAGE, PH_EPI_PLUG, PH_COUNT };
 #if defined(MJB_PHASE_PROF) && !defined(MJB_HOST_EMU)
 __device__ unsigned long long g_phase_cycles[32];
 __device__ __forceinline__ void mjb_phase(long long* t_last, int lane, int id) {
@@ -1220,7 +1221,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) done = true;
     }
     MJB_PH(c, PH_NEWTON_GRAD);
-    if (!(c.align_all ? MJB_CTA_ANY(c.cta_threads, !done) : !done)) break;
+    if (!((c.align_all & 1) ? MJB_CTA_ANY(c.cta_threads, !done) : !done)) break;
     if (done) continue;
     it++;
     // Hessian H = M + J' diag(D active) J (packed lower triangle)
@@ -1519,7 +1520,7 @@ MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out, int
   MJB_PH(c, PH_CRB);
   rne_pass(c, false);
   MJB_PH(c, PH_RNE);
-  MJB_CTA_SYNC(c.cta_threads);  // re-align the env-warps of the CTA before the data-dependent phases
+  if (c.align_all & 2) MJB_CTA_SYNC(c.cta_threads);  // re-align the env-warps of the CTA before the data-dependent phases
   MJB_PH(c, PH_ALIGN);
   int tot[MJB_MAX_PACK] = {0, 0, 0, 0};
   int ncon = collide(c, tot);
@@ -1530,12 +1531,17 @@ MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out, int
   }
   if (sensors) sensors_pos(c);
   MJB_PH(c, PH_SENS);
-  if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
+  if (c.align_all & 1) MJB_CTA_SYNC(c.cta_threads);
   make_constraints(c, ncon);
   MJB_PH(c, PH_CONSTR);
-  if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
+  if (c.align_all & 1) MJB_CTA_SYNC(c.cta_threads);
   int it = newton(c, ncon);
-  if (c.align_all) MJB_CTA_SYNC(c.cta_threads);
+  // The Newton solve is where the envs of a round drift apart (1 .. 5 iterations).  Waiting for the slowest one HERE
+  // instead of at the end of the round costs the same wait, and the rest of the step (sensors, integration, stores,
+  // epilogue) then runs with the warps walking the code together: their instruction fetches hit lines a neighbour
+  // has just brought in (the tail used to be the part with the most instruction-fetch stalls)
+  if (c.align_all & 5) MJB_CTA_SYNC(c.cta_threads);
+  MJB_PH(c, PH_ALIGN);
   if (iters_out) *iters_out = it;
   if (sensors) sensors_acc(c, ncon);
   MJB_PH(c, PH_SENS);

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "mujoco_rl_environment_wrapper_b200")
 PROF_LIB = os.path.join(PKG, "libmjb_prof.so")
 PHASES = ["load", "fk", "crb", "rne", "collide", "sensors", "constraints", "newton_init", "newton_grad", "newton_hess", "newton_factor",
-          "newton_linesearch", "integrate", "store", "epilogue", "round_barrier", "align", "ls_rowsmul", "ls_Mv", "ls_loop"]
+          "newton_linesearch", "integrate", "store", "epilogue", "round_barrier", "align", "ls_rowsmul", "ls_Mv", "ls_loop", "epi_obs", "epi_stage", "epi_plugins"]
 
 
 def build():
