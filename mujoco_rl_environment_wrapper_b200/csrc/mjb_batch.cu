@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
   // MJB_LOCKSTEP: 2 rounds only, 1 rounds + every alignment point, 3 rounds replaced by a sync before the collision phase,
-  // 4 (default) rounds + re-alignment after the Newton solve, 5 = 4 + before the collision phase
-  Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1 ? 7 : (lockstep == 3 ? 2 : (lockstep == 4 ? 4 : (lockstep == 5 ? 6 : 0)))};
+  // 4 (default) rounds + re-alignment after the Newton solve, 5 = 4 + before the collision phase, 6 = 4 + Newton iterations
+  Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1 ? 7 : (lockstep == 3 ? 2 : (lockstep == 4 ? 4 : (lockstep == 5 ? 6 : (lockstep == 6 ? 5 : 0))))};
 #if defined(MJB_PHASE_PROF)
   long long t_last = clock64();
   c.t_last = &t_last;
