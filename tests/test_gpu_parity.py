@@ -4,6 +4,8 @@ states |x_gpu - x_ref| <= 1e-4 * max(1, |x_ref|) for qpos / qvel / sensordata; c
 Language observations, termination / truncation flags and drawn targets are compared EXACTLY.
 Short-horizon drift bound: after 200 free-running steps |qpos_gpu - qpos_ref|_inf <= 5e-3 while no
 contact event is missed (contact-rich trajectories are chaotic beyond that)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -669,6 +671,33 @@ def test_parallel_api_conformance(xml, free_joint):
             assert isinstance(rew[a], (int, float)) and isinstance(term[a], bool) and isinstance(trunc[a], bool)
         assert trunc["__all__"] == (t >= 40)   # the check runs before the counter advances (mujoco_rl.py:279,288)
     assert finite_bounds > 0, "the level must declare bounded sensors"
+
+
+@pytest.mark.gpu
+def test_soak_keeps_every_contact():
+    """Random-action rollout of the two-ant level with per-env auto-reset: the cumulative count of contacts found beyond
+    an env's contact slots (mjb_buffers.ncon_dropped) stays 0, no env is reset for a non-finite state, and the state
+    stays finite.  (tools/soak.py runs the same at 65536 envs x 3000 steps -> profiles/r02_soak.json.)"""
+    from mujoco_rl_environment_wrapper_b200 import plugins as P
+    from mujoco_rl_environment_wrapper_b200.mujoco_rl import MuJoCoRL
+    lv = os.path.join(os.path.dirname(os.path.abspath(__file__)), "levels")
+    env = MuJoCoRL({"xmlPath": os.path.join(lv, "two_ants.xml"), "infoJson": os.path.join(lv, "info_2A.json"), "agents": ["sender", "receiver"],
+                    "environmentDynamics": [P.Language], "rewardFunctions": [P.tag_distance_reward], "doneFunctions": [P.distance_done],
+                    "num_envs": 2048, "maxSteps": 200, "seed": 3})
+    env.reset()
+    b = env.batch
+    max_ncon = 0
+    for t in range(600):
+        obs, rew, term, trunc, _ = env.step(env.sample_actions())
+        if t % 25 == 24:
+            max_ncon = max(max_ncon, int(b.ncon.max()))
+            done = term["__all__"] | trunc["__all__"]
+            if bool(done.any()):
+                env.reset(mask=done)
+    assert int(b.ncon_dropped.sum()) == 0
+    assert int(b.nreset.sum()) == 0
+    assert 0 < max_ncon <= b.layout.maxcon
+    assert bool(torch.isfinite(b.qpos).all() and torch.isfinite(b.qvel).all() and torch.isfinite(b.obs).all())
 
 
 # ---- narrow phase: closed-form cases and random poses through the C-ABI (the same cases run on the kernel source under

@@ -25,8 +25,9 @@ for t in range(STEPS):
             env.reset(mask=done)
 res = {"envs": N, "steps": STEPS, "finite": bool(torch.isfinite(b.qpos).all() and torch.isfinite(b.qvel).all() and torch.isfinite(b.obs).all()),
        "divergence_resets": int(b.nreset.sum()), "max_contacts_seen": max_ncon, "contact_slots": b.layout.maxcon,
+       "contacts_dropped_total": int(b.ncon_dropped.sum()),
        "max_newton_iters_seen": max_iter, "episodes_reset": episodes,
        "max_abs_qvel": float(b.qvel.abs().max()), "max_height": float(b.qpos[:, 2].max())}
 print(json.dumps(res))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r01_soak.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r02_soak.json"), "w"), indent=1)
