@@ -364,6 +364,218 @@ MJB_DEV void rne_pass(const Ctx& c, bool with_acc) {
   MJB_SYNC();
 }
 
+// ---- fused passes of the step proper -------------------------------------------------------------------------------
+// kin_forward = fk + the outward half of rne_pass in ONE walk over the tree levels: per body its frame, motion subspaces
+// (about the tree root's origin), spatial inertia, velocity, bias acceleration and its own inertial force
+// I a + v x* I v.  Composite inertias later accumulate IN PLACE in SF_cinert; SF_crb holds the body forces.
+// dyn_backward = the inward halves of crb_mass and rne_pass in one walk (16 words per body), then one loop over the dofs
+// for the rows of M and qfrc_smooth.  (fk / crb_mass / rne_pass stay for the renderer and the accelerometer pass.)
+MJB_DEV void kin_forward(const Ctx& c) {
+  const DevModel& dm = *c.dm;
+  const int* level_adr = CI(level_adr);
+  float *qpos = SF(qpos), *qvel = SF(qvel);
+  float *xpos = SF(xpos), *xquat = SF(xquat), *xmat = SF(xmat), *xipos = SF(xipos), *cdof = SF(cdof);
+  float *cinert = SF(cinert), *cfrc = SF(crb), *cvel = SF(cvel), *cacc = SF(cacc);
+  MJB_NOUNROLL
+  for (int l = 0; l < dm.nlevel; l++) {
+    MJB_NOUNROLL
+    for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
+      const int p = CI(mb_parent)[b], root = CI(mb_root)[b];
+      f3 pos = ld3(CF(mb_pos) + 3 * b);
+      q4 quat = ldq(CF(mb_quat) + 4 * b);
+      if (p >= 0) {
+        pos = ld3(xpos + 3 * p) + mulv(xmat + 9 * p, pos);
+        quat = qmul(ldq(xquat + 4 * p), quat);
+      }
+      const int ja = CI(mb_jntadr)[b], jn = CI(mb_jntnum)[b];
+      MJB_NOUNROLL
+      for (int j = ja; j < ja + jn; j++) {
+        int type = CI(jnt_type)[j], qa = CI(jnt_qposadr)[j], da = CI(jnt_dofadr)[j];
+        if (type == MJB_JNT_FREE) {
+          pos = ld3(qpos + qa);
+          quat = qnorm(ldq(qpos + qa + 3));
+          qpos[qa + 3] = quat.w; qpos[qa + 4] = quat.x; qpos[qa + 5] = quat.y; qpos[qa + 6] = quat.z;
+        } else {
+          f3 jpos = ld3(CF(jnt_pos) + 3 * j), jax = ld3(CF(jnt_axis) + 3 * j);
+          f3 anchor = pos + qrot(quat, jpos), axis = qrot(quat, jax);
+          float q = qpos[qa] - CF(jnt_qpos0)[j];
+          st3(cdof + 6 * da, axis); st3(cdof + 6 * da + 3, anchor);   // [axis; anchor] until the tree origin is known
+          if (type == MJB_JNT_HINGE) {
+            quat = qmul(quat, axisangle(jax, q));
+            pos = anchor - qrot(quat, jpos);
+          } else {
+            pos = pos + axis * q;
+          }
+        }
+      }
+      quat = qnorm(quat);
+      float R[9];
+      q2m(quat, R);
+      st3(xpos + 3 * b, pos);
+      xquat[4 * b] = quat.w; xquat[4 * b + 1] = quat.x; xquat[4 * b + 2] = quat.y; xquat[4 * b + 3] = quat.z;
+#pragma unroll
+      for (int i = 0; i < 9; i++) xmat[9 * b + i] = R[i];
+      const f3 ipos = pos + mulv(R, ld3(CF(mb_ipos) + 3 * b));
+      st3(xipos + 3 * b, ipos);
+      const f3 o = (root == b) ? pos : ld3(xpos + 3 * root);
+      MJB_NOUNROLL
+      for (int j = ja; j < ja + jn; j++) {
+        int type = CI(jnt_type)[j], da = CI(jnt_dofadr)[j];
+        if (type == MJB_JNT_FREE) {
+          for (int i = 0; i < 3; i++) {
+            st3(cdof + 6 * (da + i), mk3(0, 0, 0));
+            st3(cdof + 6 * (da + i) + 3, mk3(i == 0, i == 1, i == 2));
+            f3 ax = colv(R, i);
+            st3(cdof + 6 * (da + 3 + i), ax);
+            st3(cdof + 6 * (da + 3 + i) + 3, cross(ax, o - pos));
+          }
+        } else if (type == MJB_JNT_HINGE) {
+          f3 axis = ld3(cdof + 6 * da), anchor = ld3(cdof + 6 * da + 3);
+          st3(cdof + 6 * da + 3, cross(axis, o - anchor));
+        } else {
+          f3 axis = ld3(cdof + 6 * da);
+          st3(cdof + 6 * da, mk3(0, 0, 0)); st3(cdof + 6 * da + 3, axis);
+        }
+      }
+      // spatial inertia about the tree origin
+      float I[10];
+      {
+        float Ri[9];
+        q2m(qmul(quat, ldq(CF(mb_iquat) + 4 * b)), Ri);
+        const f3 In = ld3(CF(mb_inertia) + 3 * b);
+        const float m = CF(mb_mass)[b];
+        const f3 cc = ipos - o;
+        I[0] = m; I[1] = m * cc.x; I[2] = m * cc.y; I[3] = m * cc.z;
+        I[4] = Ri[0] * Ri[0] * In.x + Ri[1] * Ri[1] * In.y + Ri[2] * Ri[2] * In.z + m * (cc.y * cc.y + cc.z * cc.z);
+        I[5] = Ri[3] * Ri[3] * In.x + Ri[4] * Ri[4] * In.y + Ri[5] * Ri[5] * In.z + m * (cc.x * cc.x + cc.z * cc.z);
+        I[6] = Ri[6] * Ri[6] * In.x + Ri[7] * Ri[7] * In.y + Ri[8] * Ri[8] * In.z + m * (cc.x * cc.x + cc.y * cc.y);
+        I[7] = Ri[0] * Ri[3] * In.x + Ri[1] * Ri[4] * In.y + Ri[2] * Ri[5] * In.z - m * cc.x * cc.y;
+        I[8] = Ri[0] * Ri[6] * In.x + Ri[1] * Ri[7] * In.y + Ri[2] * Ri[8] * In.z - m * cc.x * cc.z;
+        I[9] = Ri[3] * Ri[6] * In.x + Ri[4] * Ri[7] * In.y + Ri[5] * Ri[8] * In.z - m * cc.y * cc.z;
+#pragma unroll
+        for (int i = 0; i < 10; i++) cinert[10 * b + i] = I[i];
+      }
+      // velocity and bias acceleration of the body (outward pass of the recursive Newton-Euler algorithm)
+      f3 w = mk3(0, 0, 0), v = mk3(0, 0, 0), aw = mk3(0, 0, 0);
+      f3 av = mk3(-dm.gravity[0], -dm.gravity[1], -dm.gravity[2]);
+      if (p >= 0) { w = ld3(cvel + 6 * p); v = ld3(cvel + 6 * p + 3); aw = ld3(cacc + 6 * p); av = ld3(cacc + 6 * p + 3); }
+      const int da = CI(mb_dofadr)[b], dn = CI(mb_dofnum)[b];
+      f3 wb = w, vb = v;  // velocity snapshot for the free joint's rotational block
+      MJB_NOUNROLL
+      for (int d = da; d < da + dn; d++) {
+        const int kind = CI(dof_kind)[d];
+        const f3 sw = ld3(cdof + 6 * d), sv = ld3(cdof + 6 * d + 3);
+        const float qd = qvel[d];
+        if (kind == DOF_FREE_ROT && d == da + 3) { wb = w; vb = v; }
+        if (kind != DOF_FREE_TRANS) {
+          const f3 uw = kind == DOF_FREE_ROT ? wb : w, uv = kind == DOF_FREE_ROT ? vb : v;
+          aw = aw + cross(uw, sw) * qd;                              // cdof_dot = u x_m S
+          av = av + (cross(uw, sv) + cross(uv, sw)) * qd;
+        }
+        w = w + sw * qd; v = v + sv * qd;
+      }
+      st3(cvel + 6 * b, w); st3(cvel + 6 * b + 3, v);
+      st3(cacc + 6 * b, aw); st3(cacc + 6 * b + 3, av);
+      {
+        f3 n1, f1, n2, f2;
+        inertia_mul(I, aw, av, n1, f1);
+        inertia_mul(I, w, v, n2, f2);
+        st3(cfrc + 10 * b, n1 + cross(w, n2) + cross(v, f2));         // v x* (I v) = [w x n + v x f ; w x f]
+        st3(cfrc + 10 * b + 3, f1 + cross(w, f2));
+      }
+    }
+    MJB_SYNC();
+  }
+  // dynamic geom frames
+  float *gpos = SF(gpos), *gmat = SF(gmat);
+  MJB_NOUNROLL
+  for (int g = c.lane; g < dm.ngeom; g += 32) {
+    int slot = CI(geom_slot)[g];
+    if (slot < 0) continue;
+    int b = CI(geom_mb)[g];
+    st3(gpos + 3 * slot, ld3(xpos + 3 * b) + mulv(xmat + 9 * b, ld3(CF(geom_pos) + 3 * g)));
+    q2m(qmul(ldq(xquat + 4 * b), ldq(CF(geom_quat) + 4 * g)), gmat + 9 * slot);
+  }
+  float *spos = SF(spos), *smat = SF(smat);
+  MJB_NOUNROLL
+  for (int t = c.lane; t < dm.nsite; t += 32) {
+    int b = CI(site_mb)[t];
+    f3 lp = ld3(CF(site_pos) + 3 * t);
+    q4 lq = ldq(CF(site_quat) + 4 * t);
+    if (b >= 0) { lp = ld3(xpos + 3 * b) + mulv(xmat + 9 * b, lp); lq = qmul(ldq(xquat + 4 * b), lq); }
+    st3(spos + 3 * t, lp);
+    q2m(lq, smat + 9 * t);
+  }
+  // M starts from zero (only ancestor pairs are written below)
+  {
+    struct alignas(16) W4 { float a, b, c, d; };
+    W4* m4 = (W4*)SF(M);
+    const W4 z = {0.f, 0.f, 0.f, 0.f};
+    MJB_NOUNROLL
+    for (int i = c.lane; i < ((dm.nv * (dm.nv + 1)) / 2 + 3) / 4; i += 32) m4[i] = z;
+  }
+  MJB_SYNC();
+}
+
+MJB_DEV void dyn_backward(const Ctx& c) {
+  const DevModel& dm = *c.dm;
+  const int* level_adr = CI(level_adr);
+  float *crb = SF(cinert), *cfrc = SF(crb), *M = SF(M), *cdof = SF(cdof), *qvel = SF(qvel);
+  MJB_NOUNROLL
+  for (int l = dm.nlevel - 2; l >= 0; l--) {
+    MJB_NOUNROLL
+    for (int b = level_adr[l] + c.lane; b < level_adr[l + 1]; b += 32) {
+      const int ca = CI(mb_childadr)[b], ce = CI(mb_childadr)[b + 1];
+      if (ce > ca) {
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 10; i++) acc[i] = crb[10 * b + i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc[10 + i] = cfrc[10 * b + i];
+        MJB_NOUNROLL
+        for (int k = ca; k < ce; k++) {
+          const int ch = CI(mb_child)[k];
+#pragma unroll
+          for (int i = 0; i < 10; i++) acc[i] += crb[10 * ch + i];
+#pragma unroll
+          for (int i = 0; i < 6; i++) acc[10 + i] += cfrc[10 * ch + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) crb[10 * b + i] = acc[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) cfrc[10 * b + i] = acc[10 + i];
+      }
+    }
+    MJB_SYNC();
+  }
+  float *qfrc = SF(qfrc), *ctrl = SF(ctrl);
+  MJB_NOUNROLL
+  for (int i = c.lane; i < dm.nv; i += 32) {
+    const int b = CI(dof_mb)[i];
+    const f3 sw = ld3(cdof + 6 * i), sv = ld3(cdof + 6 * i + 3);
+    f3 n, f;
+    inertia_mul(crb + 10 * b, sw, sv, n, f);
+    MJB_NOUNROLL
+    for (int j = i; j >= 0; j = CI(dof_parent)[j]) {
+      float v = dot(ld3(cdof + 6 * j), n) + dot(ld3(cdof + 6 * j + 3), f);
+      if (j == i) v += CF(dof_armature)[i];
+      M[tri(i, j)] = v;  // j is an ancestor dof: j <= i
+    }
+    const float bias = dot(sw, ld3(cfrc + 10 * b)) + dot(sv, ld3(cfrc + 10 * b + 3));
+    float fq = -CF(dof_damping)[i] * qvel[i] - bias;
+    MJB_NOUNROLL
+    for (int k = CI(dof_actadr)[i]; k < CI(dof_actadr)[i] + CI(dof_actnum)[i]; k++) {
+      int u = CI(act_list)[k];
+      const float* ap = CF(act_param) + 4 * u;
+      float cv = ctrl[u];
+      if (ap[1] != 0.f) cv = fminf(ap[3], fmaxf(ap[2], cv));
+      fq += ap[0] * cv;
+    }
+    qfrc[i] = fq;
+  }
+  MJB_SYNC();
+}
+
 // =================================================================================================
 // collision
 struct GeomW { f3 pos; const float* mat; const float* size; int type; };
@@ -1489,7 +1701,7 @@ MJB_DEV void sensors_acc(const Ctx& c, int ncon) {
 // one forward-dynamics evaluation: SF_qpos / qvel / ctrl -> SF_qacc.  Returns the contact count.
 MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out, int* found) {
   MJB_PH(c, PH_INTEGRATE);
-  fk(c);
+  kin_forward(c);
   if (probes) {
     // exported positions belong to the LAST forward pass of the step (what `data.xipos` holds after
     // mj_step): for Euler that is the state before the integration, for RK4 the fourth stage.
@@ -1516,9 +1728,7 @@ MJB_DEV int forward(const Ctx& c, bool sensors, bool probes, int* iters_out, int
     MJB_SYNC();
   }
   MJB_PH(c, PH_FK);
-  crb_mass(c);
-  MJB_PH(c, PH_CRB);
-  rne_pass(c, false);
+  dyn_backward(c);
   MJB_PH(c, PH_RNE);
   if (c.align_all & 2) MJB_CTA_SYNC(c.cta_threads);  // re-align the env-warps of the CTA before the data-dependent phases
   MJB_PH(c, PH_ALIGN);
