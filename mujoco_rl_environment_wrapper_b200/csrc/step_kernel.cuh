@@ -460,19 +460,27 @@ MJB_DEV void kin_forward(const Ctx& c) {
       f3 av = mk3(-dm.gravity[0], -dm.gravity[1], -dm.gravity[2]);
       if (p >= 0) { w = ld3(cvel + 6 * p); v = ld3(cvel + 6 * p + 3); aw = ld3(cacc + 6 * p); av = ld3(cacc + 6 * p + 3); }
       const int da = CI(mb_dofadr)[b], dn = CI(mb_dofnum)[b];
-      f3 wb = w, vb = v;  // velocity snapshot for the free joint's rotational block
-      MJB_NOUNROLL
-      for (int d = da; d < da + dn; d++) {
-        const int kind = CI(dof_kind)[d];
-        const f3 sw = ld3(cdof + 6 * d), sv = ld3(cdof + 6 * d + 3);
-        const float qd = qvel[d];
-        if (kind == DOF_FREE_ROT && d == da + 3) { wb = w; vb = v; }
-        if (kind != DOF_FREE_TRANS) {
-          const f3 uw = kind == DOF_FREE_ROT ? wb : w, uv = kind == DOF_FREE_ROT ? vb : v;
-          aw = aw + cross(uw, sw) * qd;                              // cdof_dot = u x_m S
-          av = av + (cross(uw, sv) + cross(uv, sw)) * qd;
+      if (p < 0 && root == b && dn == 6 && CI(dof_kind)[da] == DOF_FREE_TRANS) {
+        // free joint of a tree root (parent at rest, motion subspaces about its own origin): the six-dof loop below
+        // collapses to v = qvel[0:3], w = R qvel[3:6], bias acceleration [0 ; v x w] (only 2 of 32 lanes sit at this level)
+        v = ld3(qvel + da);
+        w = mulv(R, ld3(qvel + da + 3));
+        av = av + cross(v, w);
+      } else {
+        f3 wb = w, vb = v;  // velocity snapshot for the free joint's rotational block
+        MJB_NOUNROLL
+        for (int d = da; d < da + dn; d++) {
+          const int kind = CI(dof_kind)[d];
+          const f3 sw = ld3(cdof + 6 * d), sv = ld3(cdof + 6 * d + 3);
+          const float qd = qvel[d];
+          if (kind == DOF_FREE_ROT && d == da + 3) { wb = w; vb = v; }
+          if (kind != DOF_FREE_TRANS) {
+            const f3 uw = kind == DOF_FREE_ROT ? wb : w, uv = kind == DOF_FREE_ROT ? vb : v;
+            aw = aw + cross(uw, sw) * qd;                              // cdof_dot = u x_m S
+            av = av + (cross(uw, sv) + cross(uv, sw)) * qd;
+          }
+          w = w + sw * qd; v = v + sv * qd;
         }
-        w = w + sw * qd; v = v + sv * qd;
       }
       st3(cvel + 6 * b, w); st3(cvel + 6 * b + 3, v);
       st3(cacc + 6 * b, aw); st3(cacc + 6 * b + 3, av);
@@ -887,10 +895,21 @@ MJB_DEV int collide(const Ctx& c, int* tot) {
   }
   if (dm.nblock > 0 && dm.nblock <= 32) act_hi = 0;
   // level 2: bounding spheres of the geoms (planes: signed distance of the centre), 32 pairs per pass
+  // (which passes hold a pair of a live block is itself decided lane-parallel: lane = pass, then only those are walked)
+  const int npass = (dm.npair + 31) >> 5;
   MJB_NOUNROLL
-  for (int base = 0; base < dm.npair; base += 32) {
-    const uint32_t* pm = CU(bp_passmask) + 2 * (base >> 5);
-    if (!((pm[0] & act_lo) | (pm[1] & act_hi))) continue;   // warp-uniform
+  for (int pb = 0; pb < npass; pb += 32) {
+  uint32_t live = 0;
+  {
+    const int ps = pb + c.lane;
+    bool on = false;
+    if (ps < npass) { const uint32_t* pm = CU(bp_passmask) + 2 * ps; on = ((pm[0] & act_lo) | (pm[1] & act_hi)) != 0u; }
+    live = MJB_BALLOT(on);
+  }
+  MJB_NOUNROLL
+  while (live) {
+    const int base = (pb + MJB_FFS(live) - 1) << 5;
+    live &= live - 1u;
     int p = base + c.lane;
     bool keep = false;
     if (p < dm.npair) {
@@ -913,6 +932,7 @@ MJB_DEV int collide(const Ctx& c, int* tot) {
     int idx = ncand + MJB_POPC(bal & ((1u << c.lane) - 1u));
     if (keep && idx < dm.maxcand) cand[idx] = p;
     ncand += MJB_POPC(bal);
+  }
   }
   if (ncand > dm.maxcand) ncand = dm.maxcand;
   MJB_SYNC();
@@ -974,13 +994,28 @@ MJB_DEV int collide(const Ctx& c, int* tot) {
     }
   }
   // multi-contact types (plane-box, box-box): one candidate at a time, lane = box corner
+  // (the candidates of these types are found lane-parallel first: usually there is none)
   MJB_NOUNROLL
-  for (int i = 0; i < ncand; i++) {
+  for (int cb = 0; cb < ncand; cb += 32) {
+  uint32_t multi = 0;
+  {
+    const int i = cb + c.lane;
+    bool is_multi = false;
+    if (i < ncand) {
+      const uint32_t pk = pairs[cand[i]];
+      const int t1 = CI(geom_type)[pk & 0xfff], t2 = CI(geom_type)[(pk >> 12) & 0xfff];
+      is_multi = t2 == MJB_GEOM_BOX && (t1 == MJB_GEOM_PLANE || t1 == MJB_GEOM_BOX);
+    }
+    multi = MJB_BALLOT(is_multi);
+  }
+  MJB_NOUNROLL
+  while (multi) {
+    const int i = cb + MJB_FFS(multi) - 1;
+    multi &= multi - 1u;
     int p = cand[i];
     uint32_t pk = pairs[p];
     int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
-    int t1 = CI(geom_type)[g1], t2 = CI(geom_type)[g2];
-    if (t2 != MJB_GEOM_BOX || (t1 != MJB_GEOM_PLANE && t1 != MJB_GEOM_BOX)) continue;  // warp-uniform
+    int t1 = CI(geom_type)[g1];
     const float* pc = CF(pclass) + PC_STRIDE * (pk >> 24);
     float margin = pc[PC_MARGIN], mu = pc[PC_MU];
     GeomW a = geom_world(c, g1), b = geom_world(c, g2);
@@ -1016,6 +1051,7 @@ MJB_DEV int collide(const Ctx& c, int* tot) {
     if (add > room) add = room;
     if (hit && rank < add) store_contact(c, ncon + rank, o, p, mu);
     ncon += add;
+  }
   }
   MJB_SYNC();
   return ncon;
