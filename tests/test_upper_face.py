@@ -233,3 +233,47 @@ def test_get_data_orientation_and_arbitrary_names():
     env_all.reset()
     env_all.step(env_all.sample_actions())
     assert env_all.distance("aux_4_2", "back_leg").shape == (2,)
+
+
+@pytest.mark.gpu
+def test_done_threshold_and_reward_are_the_references_fp64_arithmetic():
+    """Agents placed within +-1e-6 of the done threshold (distance 1 to their target): the done flag and the reward are
+    exactly what the reference's arithmetic (math.dist on float64 views, README.md:149-173) gives on the fp32 positions
+    the step exported — d <= 1 decided in fp64, reward = float32(10 * (d_prev - d))."""
+    N, A = 512, 2
+    env = _env(num_envs=N, seed=17, environmentDynamics=[P.Language], rewardFunctions=[P.tag_distance_reward], doneFunctions=[P.distance_done])
+    env.reset()
+    b = env.batch
+    env.step(env.sample_actions())          # first call per agent: target drawn, distance stored, reward 0
+    torch.cuda.synchronize()
+    names = env._probe_names
+    tgt_probe = torch.tensor([names.index(t) for t in env._target_names], device=env.device)
+    rows = torch.arange(N, device=env.device)
+    deltas = torch.linspace(-1e-6, 1e-6, N, device=env.device, dtype=torch.float64)
+    d_prev, tgt_idx = {}, {}
+    for a in range(A):
+        tgt = b.store_i[:, a, L.STORE_I["current_target"]].long() - 1
+        assert bool((tgt >= 0).all())
+        tgt_idx[a] = tgt_probe[tgt]
+        tp = b.probe[rows, tgt_idx[a], :3].double()
+        pos = b.qpos[:, 15 * a:15 * a + 3].double()
+        u = pos - tp
+        u = u / u.norm(dim=1, keepdim=True)
+        b.qpos[:, 15 * a:15 * a + 3] = (tp + u * (1.0 + deltas)[:, None]).float()
+        d_prev[a] = b.store_f.view(torch.float64)[:, a, 1].clone()
+    obs, rew, term, trunc, _ = env.step(env.sample_actions())
+    torch.cuda.synchronize()
+    probe = b.probe.cpu().numpy()
+    both = set()
+    for a, name in enumerate(env.agents):
+        pa = probe[:, a, :3].astype(np.float64)
+        pt = probe[np.arange(N), tgt_idx[a].cpu().numpy(), :3].astype(np.float64)
+        dx, dy, dz = (pa - pt).T
+        d = np.sqrt((dx * dx + dy * dy) + dz * dz)
+        assert np.abs(d - 1.0).max() < 5e-6, "the agents must sit at the threshold"
+        want_done = d <= 1.0
+        want_rew = (10.0 * (d_prev[a].cpu().numpy() - d)).astype(np.float32)
+        assert np.array_equal(term[name].cpu().numpy(), want_done), name
+        assert np.array_equal(rew[name].cpu().numpy(), want_rew), name
+        both |= set(want_done.tolist())
+    assert both == {True, False}, "both sides of the threshold must occur"
