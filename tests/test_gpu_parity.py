@@ -794,3 +794,54 @@ def test_literal_step_tile_kernel_matches_host_loop(scene, n):
             assert bool(trunc["__all__"][e]) == mtrunc["__all__"]
         assert bool(trunc["__all__"][0]) == (t >= max_steps)
     assert int(env.batch.timestep[n - 1]) == 12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,N,roll", [("2A", 65536, 320), ("1A", 65536, 80), ("S3", 16384, 320), ("3S", 16384, 320)])
+def test_baseline_sizes_strided_subset_against_oracle(scene, N, roll):
+    """One step from identical states AT the BASELINE env counts (C2 / C3 at 65536, C4 at 16384): the full batch runs a
+    random-action rollout on the GPU (every env its own actions, so the states spread out), then 48 envs strided
+    across the whole grid — every CTA position, first and last env, all copies of a packed warp — are stepped once more
+    and compared with the fp64 oracle started from their (downloaded) pre-step states.  Same tolerance and exact contact-pair
+    sets as test_one_step_parity."""
+    model, tables, agents, fj = load_scene(scene)
+    spec, keep = make_spec(model, tables, agents, fj)
+    b = _batch(model, spec, N, keep)
+    nq, nv, nu, ns, n_phys, A = model.nq, model.nv, model.nu, model.nsensordata, spec.n_phys_act, len(agents)
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    b.reset()
+    for k in range(roll):
+        b.actions[:, :, :n_phys] = torch.rand((N, A, n_phys), generator=g, device="cuda") * 2 - 1
+        b.physics(1)
+    b.sync()
+    sub = np.unique(np.concatenate([np.arange(0, N, N // 40), [1, 2, 3, N - 3, N - 2, N - 1]]))
+    pre = {k: getattr(b, k)[sub].cpu().numpy().astype(np.float64) for k in ("qpos", "qvel", "warmstart", "ctrl")}
+    act = (torch.rand((N, A, n_phys), generator=g, device="cuda") * 2 - 1)
+    b.actions[:, :, :n_phys] = act
+    act_np = act[sub].cpu().numpy().astype(np.float64)
+    b.physics(1); b.sync()
+    q, v, sens = b.qpos[sub].cpu().numpy(), b.qvel[sub].cpu().numpy(), b.sensordata[sub].cpu().numpy()
+    ncon, cg = b.ncon[sub].cpu().numpy(), b.contact_geom[sub].cpu().numpy()
+    assert len({tuple(np.round(r, 3)) for r in pre["qpos"][:, :nq]}) > len(sub) // 2, "the envs must have spread out"
+    sim = OracleSim(model.blob)
+    contacts = 0
+    for i, e in enumerate(sub):
+        sim.reset()
+        sim.qpos[:] = pre["qpos"][i, :nq]; sim.qvel[:] = pre["qvel"][i, :nv]; sim.qacc_warmstart[:] = pre["warmstart"][i, :nv]
+        if nu:
+            sim.ctrl[:] = pre["ctrl"][i, :nu]
+        for a, agent in enumerate(agents):
+            idx = tables.agents_action_index[agent]
+            if fj:
+                sim.qvel[idx] = act_np[i, a]
+            else:
+                sim.ctrl[idx] = act_np[i, a]
+        sim.step()
+        assert rel_err(q[i, :nq], sim.qpos) < RTOL, (scene, int(e))
+        assert rel_err(v[i, :nv], sim.qvel) < RTOL, (scene, int(e))
+        if ns:
+            assert rel_err(sens[i, :ns], sim.sensordata[:ns]) < 2e-3, (scene, int(e))
+        assert sorted((int(x), int(y)) for x, y in cg[i, :ncon[i]]) == sorted(sim.contact_pairs()), (scene, int(e))
+        contacts += int(ncon[i])
+    assert contacts > 0
+    assert int(b.ncon_dropped.sum()) == 0
