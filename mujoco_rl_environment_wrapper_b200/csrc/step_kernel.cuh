@@ -1111,15 +1111,16 @@ MJB_DEV void make_constraints(const Ctx& c, int ncon) {
     int b1 = CI(geom_mb)[pk & 0xfff], b2 = CI(geom_mb)[(pk >> 12) & 0xfff];
     uint32_t mask = (b1 >= 0 ? CU(mb_dofmask)[2 * b1] : 0u) ^ (b2 >= 0 ? CU(mb_dofmask)[2 * b2] : 0u);
     ((uint32_t*)r)[CON_MASK] = mask;
-    uint32_t words[4] = {0u, 0u, 0u, 0u};
-    int m = 0;
-    MJB_NOUNROLL
-    while (mask && m < 16) {
-      words[m >> 2] |= (uint32_t)(MJB_FFS(mask) - 1) << (8 * (m & 3));
-      mask &= mask - 1;
-      m++;
+    // the dofs of the mask as packed bytes, ascending (four words built in registers, no indexed local array)
+#pragma unroll
+    for (int wi = 0; wi < 4; wi++) {
+      uint32_t word = 0u;
+#pragma unroll
+      for (int bi = 0; bi < 4; bi++) {
+        if (mask) { word |= (uint32_t)(MJB_FFS(mask) - 1) << (8 * bi); mask &= mask - 1; }
+      }
+      ((uint32_t*)r)[CON_DOFS + wi] = word;
     }
-    for (int i = 0; i < 4; i++) ((uint32_t*)r)[CON_DOFS + i] = words[i];
   }
   MJB_SYNC();
   MJB_NOUNROLL
@@ -1482,11 +1483,12 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       for (int i = lane; i < ((nv * (nv + 1)) / 2 + 3) / 4; i += 32) dst[i] = src[i];
     }
     MJB_SYNC();
+    // active limit rows only touch the diagonal: handed to the factorisation as the lane's diagonal term
+    float hdiag = 0.f;
     {
       const int mylim = CI(dof_lim)[lane];
-      if (mylim >= 0) H[tri(lane, lane)] += (jar[2 * mylim] < 0 ? D[2 * mylim] : 0.f) + (jar[2 * mylim + 1] < 0 ? D[2 * mylim + 1] : 0.f);
+      if (mylim >= 0) hdiag = (jar[2 * mylim] < 0 ? D[2 * mylim] : 0.f) + (jar[2 * mylim + 1] < 0 ? D[2 * mylim + 1] : 0.f);
     }
-    MJB_SYNC();
     bool coupled = false;  // does an active contact couple two kinematic trees?
     MJB_NOUNROLL
     for (int k = 0; k < ncon; k++) {
@@ -1518,7 +1520,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     // factor per tree block unless a contact couples trees (then one block over all dofs)
     const int h0 = coupled ? 0 : t0, h1 = coupled ? (lane < nv ? nv : 0) : t1, hb = coupled ? nv : dm.maxtree;
     MJB_PH(c, PH_NEWTON_HESS);
-    float s = factor_solve(H, H, lane, h0, h1, hb, 0.f, -g, nv);
+    float s = factor_solve(H, H, lane, h0, h1, hb, hdiag, -g, nv);
     if (lane < nv) sv[lane] = s; else s = 0.f;
     MJB_SYNC();
     MJB_PH(c, PH_NEWTON_FACTOR);
@@ -1569,7 +1571,13 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
       jar[r] = xn;
       frc[r] = xn < 0.f ? -d * xn : 0.f;
       jv[r] = ((xo < 0.f) != (xn < 0.f)) ? d * fabsf(xn) : 0.f;
+#if defined(MJB_PHASE_PROF) && !defined(MJB_HOST_EMU)
+      if (((xo < 0.f) != (xn < 0.f)) && d > 0.f) atomicAdd(&g_phase_cycles[25 + (it < 5 ? it : 5)], 1ull);   // switched rows by iteration (slots 26..30)
+#endif
     }
+#if defined(MJB_PHASE_PROF) && !defined(MJB_HOST_EMU)
+    if (lane == 0 && alpha == 1.f) atomicAdd(&g_phase_cycles[31], 1ull);   // steps that ended at alpha = 1
+#endif
     MJB_SYNC();
     if (lane < nv) {
       float gu, q;

@@ -53,7 +53,9 @@ def main():
         tot = sum(buf[i] for i in range(nph))
         rec = {"envs": n, "cycles_per_env_step": tot / (n * steps), "niter_mean": float(b.niter.float().mean()), "ncon_mean": float(b.ncon.float().mean()),
                "phases": {PHASES[i]: round(buf[i] / tot, 4) for i in range(nph)},
-               "linesearch_evals_per_newton_iter": buf[24] / max(1, buf[25]), "newton_iters_per_env_step": buf[25] / (n * steps)}
+               "linesearch_evals_per_newton_iter": buf[24] / max(1, buf[25]), "newton_iters_per_env_step": buf[25] / (n * steps),
+               "rows_switched_after_iteration": {str(i): buf[25 + i] / (n * steps) for i in range(1, 6)},
+               "steps_with_alpha_1": buf[31] / max(1, buf[25])}
         print(json.dumps(rec), flush=True)
         out.append(rec)
         del env, b
