@@ -1632,19 +1632,22 @@ MJB_DEV float ray_geom(f3 pos, const float* R, const float* size, f3 pnt, f3 vec
     }
     return best;
   }
-  // box
+  // box, by slabs: the same first non-negative crossing as testing the six faces one by one (origin outside: entry point,
+  // inside: exit point), a sixth of the branches
+  float tn = -MJB_BIG, tf = MJB_BIG;
+#pragma unroll
   for (int a = 0; a < 3; a++) {
-    float lva = comp(lv, a), lpa = comp(lp, a);
-    if (fabsf(lva) < MJB_MINVAL) continue;
-    int a1 = (a + 1) % 3, a2 = (a + 2) % 3;
-    for (int sg = -1; sg <= 1; sg += 2) {
-      float t = (sg * size[a] - lpa) / lva;
-      if (t < 0) continue;
-      if (fabsf(comp(lp, a1) + t * comp(lv, a1)) <= size[a1] && fabsf(comp(lp, a2) + t * comp(lv, a2)) <= size[a2])
-        if (best < 0 || t < best) best = t;
+    const float p = comp(lp, a), v = comp(lv, a), sz = size[a];
+    if (fabsf(v) < MJB_MINVAL) {
+      if (fabsf(p) > sz) return -1.f;
+    } else {
+      const float inv = 1.f / v, t1 = (-sz - p) * inv, t2 = (sz - p) * inv;
+      tn = fmaxf(tn, fminf(t1, t2));
+      tf = fminf(tf, fmaxf(t1, t2));
     }
   }
-  return best;
+  if (tn > tf || tf < 0.f) return -1.f;
+  return tn >= 0.f ? tn : tf;
 }
 
 MJB_DEV float cutoff(const Ctx& c, int i, float x) {
