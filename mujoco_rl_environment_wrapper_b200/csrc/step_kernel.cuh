@@ -1313,15 +1313,18 @@ MJB_DEV_NOINLINE float factor_solve_regT(const float* A, float* Lout, int lane, 
   x *= rdi;   // D z = y
   MJB_SYNC();
   // L' x = z: column k of L' is row k of L, contiguous across lanes in the packed store
-  const int colbase = tri(t0, 0) + lane;  // &L(t0 + kk, lane) = colbase + kk * t0 + kk (kk + 1) / 2
+  // (&L(k, lane) walks down by k words per step; lanes outside the block, or at / past column k, read a valid dummy
+  // word and keep x: branch-free)
+  const int nrow = t1 - t0, lq = own ? li : NBT;
+  const float* lp = Lout + tri(t0 + NBT - 1, 0) + lane;
 #pragma unroll
   for (int kk = NBT - 1; kk >= 1; kk--) {
     const int k = t0 + kk;
     const float xk = MJB_SHFL(x, k);
-    // branch-free: lanes outside the block (or at / past column k) read a valid dummy word and keep x
-    const bool in = own && k < t1 && lane < k;
-    const float lk = Lout[in ? colbase + kk * t0 + (kk * (kk + 1)) / 2 : 0];
+    const bool in = lq < kk && kk < nrow;
+    const float lk = *(in ? lp : Lout);
     x = in ? x - lk * xk : x;
+    lp -= k;
   }
   return x;
 }
@@ -1355,27 +1358,30 @@ MJB_DEV void rows_mul(const Ctx& c, int ncon, const float* x, float* out, const 
   }
   const float* J = SF(J);
   const float* con = SF(con);
-  int base = 2 * dm.nlim;
+  const int base = 2 * dm.nlim;
+  // contact rows: eight lanes per contact (four contacts per pass), each lane the dof slots l8, l8 + 8 of the contact's
+  // chain list; three xor-shuffles sum the normal / tangent products over the group, lanes 0..3 of the group then write
+  // the four pyramid edges n +- mu t1, n +- mu t2
   MJB_NOUNROLL
-  for (int r = c.lane; r < 3 * ncon; r += 32) {
-    float s0 = 0.f;
-    const float* jr = J + r * dm.ldj;
-    uint32_t mm = ((const uint32_t*)(con + CON_STRIDE * (r / 3)))[CON_MASK];
-    MJB_NOUNROLL
-    while (mm) {
-      s0 += *jr++ * x[MJB_FFS(mm) - 1];
-      mm &= mm - 1;
+  for (int k0 = 0; k0 < ncon; k0 += 4) {
+    const int k = k0 + (c.lane >> 3), l8 = c.lane & 7;
+    float sn = 0.f, s1 = 0.f, s2 = 0.f;
+    if (k < ncon) {
+      const uint32_t* rec = (const uint32_t*)(con + CON_STRIDE * k);
+      const int nb = MJB_POPC(rec[CON_MASK]);
+      const float *Jn = J + (3 * k) * dm.ldj, *J1 = Jn + dm.ldj, *J2 = J1 + dm.ldj;
+      MJB_NOUNROLL
+      for (int m = l8; m < nb; m += 8) {
+        const float xv = x[(rec[CON_DOFS + (m >> 2)] >> (8 * (m & 3))) & 0xff];
+        sn += Jn[m] * xv; s1 += J1[m] * xv; s2 += J2[m] * xv;
+      }
     }
-    out[base + 4 * (r / 3) + (r % 3)] = s0;
-  }
-  MJB_SYNC();
-  MJB_NOUNROLL
-  for (int k = c.lane; k < ncon; k += 32) {
-    float mu = con[CON_STRIDE * k + CON_MU];
-    float n = out[base + 4 * k], t1 = out[base + 4 * k + 1], t2 = out[base + 4 * k + 2];
-    for (int e = 0; e < 4; e++) {
-      float v = n + ((e & 1) ? -mu : mu) * (e < 2 ? t1 : t2);
-      out[base + 4 * k + e] = v - (sub ? sub[base + 4 * k + e] : 0.f);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { sn += MJB_SHFL_XOR(sn, o); s1 += MJB_SHFL_XOR(s1, o); s2 += MJB_SHFL_XOR(s2, o); }
+    if (k < ncon && l8 < 4) {
+      const float mu = con[CON_STRIDE * k + CON_MU];
+      const float v = sn + ((l8 & 1) ? -mu : mu) * (l8 < 2 ? s1 : s2);
+      out[base + 4 * k + l8] = v - (sub ? sub[base + 4 * k + l8] : 0.f);
     }
   }
   MJB_SYNC();
@@ -1459,14 +1465,19 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
   }
   MJB_PH(c, PH_NEWTON_INIT);
   int it = 0;
-  bool stalled = false, done = false;
+  bool done = false;
+  float last_step = 0.f;   // |alpha s| of the previous iteration (lane = dof)
   MJB_NOUNROLL
   for (;;) {
     // Iterations can be aligned across the env-warps of the CTA (c.align_all: they then share instruction-cache
     // lines); a warp whose env has converged idles at the barrier until every env of the round is done.
     if (!done) {
       const float qf = lane < nv ? qfrc[lane] : 0.f, ma = lane < nv ? tot[lane] + g : 0.f;   // M a = qfrc_smooth + J' f + g
+      // (four independent reductions in one stage: gradient and force norms, and the size of the previous step against
+      // the iterate for the stall test)
       const float gn = wsum(g * g), fn = wsum(qf * qf + ma * ma);
+      const float amax = wmax(lane < nv ? fabsf(a[lane]) : 0.f), smax = wmax(last_step);
+      const bool stalled = it > 0 && smax <= 1e-7f * (1.f + amax);
       if (gn <= dm.solver_tol * dm.solver_tol * (fn + 1e-12f) || it >= dm.solver_iterations || stalled) done = true;
     }
     MJB_PH(c, PH_NEWTON_GRAD);
@@ -1561,8 +1572,7 @@ MJB_DEV int newton(const Ctx& c, int ncon) {
     }
     MJB_COUNT(c, 25, 1);     // Newton iterations
     MJB_PH(c, PH_LS_LOOP);
-    float amax = wmax(lane < nv ? fabsf(a[lane]) : 0.f), smax = wmax(fabsf(alpha * s));
-    stalled = smax <= 1e-7f * (1.f + amax);
+    last_step = fabsf(alpha * s);
     if (lane < nv) a[lane] += alpha * s;
     // rows: new residual, new force, and the switched rows' term of the gradient update (kept in jv)
     MJB_NOUNROLL
