@@ -1333,9 +1333,65 @@ MJB_DEV float factor_solve_reg(const float* A, float* Lout, int lane, int t0, in
   if (nb <= 14) return factor_solve_regT<14>(A, Lout, lane, t0, t1, diag_add, b);
   return factor_solve_regT<MJB_NB>(A, Lout, lane, t0, t1, diag_add, b);
 }
+// ONE block over all dofs (a contact couples the kinematic trees, or a single large tree), up to NBT <= 32 rows:
+// register-resident Cholesky L L' with one array per lane (the L D L' form above needs two, 2 x 28 registers do not
+// fit): lane i keeps row i, column j is finished with the row of lane j broadcast by shuffles.  No shared-memory
+// traffic and no barrier inside the factorisation; L goes to `Lout` (packed) once, for the transposed solve.
+template <int NBT>
+MJB_DEV_NOINLINE float chol_solve_regT(const float* A, float* Lout, int lane, int n, float diag_add, float b) {
+  float l[NBT];
+  const bool own = lane < n;
+  const int rowoff = own ? tri(lane, 0) : 0;
+#pragma unroll
+  for (int k = 0; k < NBT; k++) {
+    float v = (own && k <= lane) ? A[rowoff + k] : 0.f;
+    l[k] = (k == lane) ? v + diag_add : v;
+  }
+  float rinv = 1.f;   // 1 / L_ii of the lane's own row
+#pragma unroll
+  for (int j = 0; j < NBT; j++) {
+    float s0 = l[j], s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < j; k++) {
+      const float ljk = MJB_SHFL(l[k], j);
+      if (k & 1) s1 -= l[k] * ljk; else s0 -= l[k] * ljk;
+    }
+    const float s = s0 + s1;
+    const float inv = MJB_RSQRT(fmaxf(MJB_SHFL(s, j), 1e-20f));
+    l[j] = s * inv;                       // L_ij for i >= j (lanes above the diagonal carry unused values)
+    if (lane == j) rinv = inv;
+  }
+  MJB_SYNC();   // every lane has read its row of A before L overwrites it (A and Lout may be the same buffer)
+#pragma unroll
+  for (int k = 0; k < NBT; k++)
+    if (own && k <= lane) Lout[rowoff + k] = l[k];
+  // L y = b
+  float x = b;
+#pragma unroll
+  for (int k = 0; k < NBT; k++) {
+    const float yk = MJB_SHFL(x * rinv, k);
+    x = lane > k ? x - l[k] * yk : x;
+  }
+  x *= rinv;
+  MJB_SYNC();
+  // L' z = y: column k of L' is row k of L, contiguous across lanes in the packed store
+#pragma unroll
+  for (int k = NBT - 1; k >= 1; k--) {
+    const float zk = MJB_SHFL(x * rinv, k);
+    const bool in = lane < k && k < n;
+    const float lk = Lout[in ? tri(k, 0) + lane : 0];
+    x = in ? x - lk * zk : x;
+  }
+  return x * rinv;
+}
+
 // (A + diag) x = b per block; picks the register path when the blocks are small enough
 MJB_DEV float factor_solve(const float* A, float* L, int lane, int t0, int t1, int nb, float diag_add, float b, int nv) {
   if (MJB_LIKELY(nb <= MJB_NB)) return factor_solve_reg(A, L, lane, t0, t1, nb, diag_add, b);
+  if (nb == nv) {   // a single block over all dofs
+    if (nv <= 28) return chol_solve_regT<28>(A, L, lane, nv, diag_add, b);
+    return chol_solve_regT<32>(A, L, lane, nv, diag_add, b);
+  }
   if (A != L) {
     MJB_NOUNROLL
     for (int i = lane; i < (nv * (nv + 1)) / 2; i += 32) L[i] = A[i];

@@ -268,3 +268,44 @@ def test_two_level_broad_phase_never_drops_a_contact():
 def OracleSimLazy(model):
     from oracle.sim import OracleSim
     return OracleSim(model.blob)
+
+
+def test_inter_ant_contacts_single_block_factorisation():
+    """Ants dropped onto each other: contacts between the two kinematic trees couple them in the Newton Hessian, which is
+    then ONE 28 x 28 block (register Cholesky over all dofs instead of two 14 x 14 L D L' blocks).  One step from identical
+    states vs the oracle, kernel source on the emulator."""
+    from oracle import OracleSim
+    model, tables, agents, fj = load_scene("2A")
+    spec, keep = make_spec(model, tables, agents, fj)
+    sim = OracleSim(model.blob)
+    rng = np.random.default_rng(21)
+    idx = np.array(tables.agents_action_index["sender"] + tables.agents_action_index["receiver"])
+    geom_body, root = model.fields["geom_bodyid"], model.fields["body_rootid"]
+    states, cross = [], 0
+    for trial in range(3):
+        sim.reset()
+        sim.qpos[15:18] = sim.qpos[0:3] + np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), 0.45 + 0.2 * rng.random()])
+        yaw = rng.uniform(0, np.pi)
+        sim.qpos[18:22] = [np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
+        for t in range(200):
+            c = rng.uniform(-1, 1, 16)
+            sim.ctrl[idx] = c
+            if t >= 60 and t % 20 == 0:
+                pre = (sim.qpos.copy(), sim.qvel.copy(), sim.qacc_warmstart.copy(), sim.ctrl.copy(), c.reshape(2, 8).copy())
+                sim.step()
+                pairs = sim.contact_pairs()
+                cross += any(root[geom_body[a]] != root[geom_body[b]] and root[geom_body[a]] and root[geom_body[b]] for a, b in pairs)
+                states.append((pre, {"qpos": sim.qpos.copy(), "qvel": sim.qvel.copy(), "pairs": sorted(pairs)}))
+            else:
+                sim.step()
+    assert cross > 5, cross
+    eb = E.EmuBatch(model.blob, spec, len(states), keep)
+    for e, (pre, post) in enumerate(states):
+        eb.qpos[e, :30], eb.qvel[e, :28], eb.warmstart[e, :28] = pre[0], pre[1], pre[2]
+        eb.ctrl[e, :16] = pre[3]
+        eb.actions[e, :, :8] = pre[4]
+    eb.run(E.MODE_PHYSICS, 1)
+    for e, (pre, post) in enumerate(states):
+        assert rel_err(eb.qpos[e, :30], post["qpos"]) < RTOL, e
+        assert rel_err(eb.qvel[e, :28], post["qvel"]) < RTOL, e
+        assert sorted((int(a), int(b)) for a, b in eb.contact_geom[e, :eb.ncon[e]]) == post["pairs"], e

@@ -56,9 +56,16 @@ def main():
     pool = torch.stack([env.sample_actions() for _ in range(16)])
     zero = torch.zeros_like(pool[0])
     zero[:, :, 8] = 1.0   # Language action stays valid
+    only_stacked = os.environ.get("ONLY") == "stacked"
     # 1. airborne: right after reset the ants are still falling
     env.reset()
-    out.append(dict(state="airborne (first steps after reset, random actions)", **timed(env, lambda k: pool[k % 16], steps=10)))
+    if not only_stacked:
+        out.append(dict(state="airborne (first steps after reset, random actions)", **timed(env, lambda k: pool[k % 16], steps=10)))
+        states_1_to_4(env, b, ad, pool, zero, out)
+    stacked(env, b, ad, pool, out)
+
+
+def states_1_to_4(env, b, ad, pool, zero, out):
     # 2. the bench's state: 300 random-action steps
     env.reset()
     for k in range(300):
@@ -78,6 +85,9 @@ def main():
     for k in range(300):
         b.actions[:, :, :ad] = push2; b.step()
     out.append(dict(state="constant full negative torque on every motor (settled 300 steps)", **timed(env, lambda k: push2)))
+
+
+def stacked(env, b, ad, pool, out):
     # 5. the two ants of every env stacked: contacts couple the two kinematic trees
     env.reset()
     torch.cuda.synchronize()
@@ -93,7 +103,7 @@ def main():
         print(json.dumps(r), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump({"envs": N, "workload": "C2 (two ants, Language + tag reward + done)", "l2": "flushed between steps", "rows": out},
-              open(os.path.join(ROOT, "gpurun_out", "r02_contacts.json"), "w"), indent=1)
+              open(os.path.join(ROOT, "gpurun_out", "r02_contacts_stacked.json" if os.environ.get("ONLY") == "stacked" else "r02_contacts.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
