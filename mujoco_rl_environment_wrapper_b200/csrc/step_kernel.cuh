@@ -437,24 +437,6 @@ MJB_DEV void kin_forward(const Ctx& c) {
           st3(cdof + 6 * da, mk3(0, 0, 0)); st3(cdof + 6 * da + 3, axis);
         }
       }
-      // spatial inertia about the tree origin
-      float I[10];
-      {
-        float Ri[9];
-        q2m(qmul(quat, ldq(CF(mb_iquat) + 4 * b)), Ri);
-        const f3 In = ld3(CF(mb_inertia) + 3 * b);
-        const float m = CF(mb_mass)[b];
-        const f3 cc = ipos - o;
-        I[0] = m; I[1] = m * cc.x; I[2] = m * cc.y; I[3] = m * cc.z;
-        I[4] = Ri[0] * Ri[0] * In.x + Ri[1] * Ri[1] * In.y + Ri[2] * Ri[2] * In.z + m * (cc.y * cc.y + cc.z * cc.z);
-        I[5] = Ri[3] * Ri[3] * In.x + Ri[4] * Ri[4] * In.y + Ri[5] * Ri[5] * In.z + m * (cc.x * cc.x + cc.z * cc.z);
-        I[6] = Ri[6] * Ri[6] * In.x + Ri[7] * Ri[7] * In.y + Ri[8] * Ri[8] * In.z + m * (cc.x * cc.x + cc.y * cc.y);
-        I[7] = Ri[0] * Ri[3] * In.x + Ri[1] * Ri[4] * In.y + Ri[2] * Ri[5] * In.z - m * cc.x * cc.y;
-        I[8] = Ri[0] * Ri[6] * In.x + Ri[1] * Ri[7] * In.y + Ri[2] * Ri[8] * In.z - m * cc.x * cc.z;
-        I[9] = Ri[3] * Ri[6] * In.x + Ri[4] * Ri[7] * In.y + Ri[5] * Ri[8] * In.z - m * cc.y * cc.z;
-#pragma unroll
-        for (int i = 0; i < 10; i++) cinert[10 * b + i] = I[i];
-      }
       // velocity and bias acceleration of the body (outward pass of the recursive Newton-Euler algorithm)
       f3 w = mk3(0, 0, 0), v = mk3(0, 0, 0), aw = mk3(0, 0, 0);
       f3 av = mk3(-dm.gravity[0], -dm.gravity[1], -dm.gravity[2]);
@@ -484,15 +466,37 @@ MJB_DEV void kin_forward(const Ctx& c) {
       }
       st3(cvel + 6 * b, w); st3(cvel + 6 * b + 3, v);
       st3(cacc + 6 * b, aw); st3(cacc + 6 * b + 3, av);
-      {
-        f3 n1, f1, n2, f2;
-        inertia_mul(I, aw, av, n1, f1);
-        inertia_mul(I, w, v, n2, f2);
-        st3(cfrc + 10 * b, n1 + cross(w, n2) + cross(v, f2));         // v x* (I v) = [w x n + v x f ; w x f]
-        st3(cfrc + 10 * b + 3, f1 + cross(w, f2));
-      }
     }
     MJB_SYNC();
+  }
+  // What does not travel along the tree runs ONCE over all bodies (lane = body) instead of once per level with a
+  // handful of live lanes: spatial inertia about the tree origin and the body's inertial force I a + v x* (I v)
+  MJB_NOUNROLL
+  for (int b = c.lane; b < level_adr[dm.nlevel]; b += 32) {
+    const f3 ipos = ld3(xipos + 3 * b), o = ld3(xpos + 3 * CI(mb_root)[b]);
+    float I[10];
+    {
+      float Ri[9];
+      q2m(qmul(ldq(xquat + 4 * b), ldq(CF(mb_iquat) + 4 * b)), Ri);
+      const f3 In = ld3(CF(mb_inertia) + 3 * b);
+      const float m = CF(mb_mass)[b];
+      const f3 cc = ipos - o;
+      I[0] = m; I[1] = m * cc.x; I[2] = m * cc.y; I[3] = m * cc.z;
+      I[4] = Ri[0] * Ri[0] * In.x + Ri[1] * Ri[1] * In.y + Ri[2] * Ri[2] * In.z + m * (cc.y * cc.y + cc.z * cc.z);
+      I[5] = Ri[3] * Ri[3] * In.x + Ri[4] * Ri[4] * In.y + Ri[5] * Ri[5] * In.z + m * (cc.x * cc.x + cc.z * cc.z);
+      I[6] = Ri[6] * Ri[6] * In.x + Ri[7] * Ri[7] * In.y + Ri[8] * Ri[8] * In.z + m * (cc.x * cc.x + cc.y * cc.y);
+      I[7] = Ri[0] * Ri[3] * In.x + Ri[1] * Ri[4] * In.y + Ri[2] * Ri[5] * In.z - m * cc.x * cc.y;
+      I[8] = Ri[0] * Ri[6] * In.x + Ri[1] * Ri[7] * In.y + Ri[2] * Ri[8] * In.z - m * cc.x * cc.z;
+      I[9] = Ri[3] * Ri[6] * In.x + Ri[4] * Ri[7] * In.y + Ri[5] * Ri[8] * In.z - m * cc.y * cc.z;
+#pragma unroll
+      for (int i = 0; i < 10; i++) cinert[10 * b + i] = I[i];
+    }
+    const f3 w = ld3(cvel + 6 * b), v = ld3(cvel + 6 * b + 3), aw = ld3(cacc + 6 * b), av = ld3(cacc + 6 * b + 3);
+    f3 n1, f1, n2, f2;
+    inertia_mul(I, aw, av, n1, f1);
+    inertia_mul(I, w, v, n2, f2);
+    st3(cfrc + 10 * b, n1 + cross(w, n2) + cross(v, f2));         // v x* (I v) = [w x n + v x f ; w x f]
+    st3(cfrc + 10 * b + 3, f1 + cross(w, f2));
   }
   // dynamic geom frames
   float *gpos = SF(gpos), *gmat = SF(gmat);
