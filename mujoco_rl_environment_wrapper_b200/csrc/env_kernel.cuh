@@ -3,6 +3,14 @@
 // reward, truncation, done — MuJoCo_Gym/mujoco_rl.py:243-289 and the reset path :291-331).
 #pragma once
 #include "step_kernel.cuh"
+#if defined(MJB_HOST_EMU)
+#define MJB_IMG_WAIT(c) ((void)0)
+#else
+#include "tma_prims.cuh"
+// the model image travels into shared memory by one bulk copy per launch; an env's row loads do not need it, so the
+// first env of a warp requests its rows first and waits for the image after
+#define MJB_IMG_WAIT(c) do { if ((c).img_bar) mbar_wait((c).img_bar, 0); } while (0)
+#endif
 
 namespace mjb {
 
@@ -214,6 +222,8 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
       if (!(mode == MODE_RESET && reset_mask && !reset_mask[e0 + k])) upd |= 1u << k;
     }
   if (!upd) return;
+  // the loads below read the image only for copies that start from qpos0 or hold no env
+  if (mode == MODE_RESET || live != (K >= 32 ? 0xffffffffu : (1u << K) - 1u)) MJB_IMG_WAIT(c);
   float *qpos = SF(qpos), *qvel = SF(qvel), *qacc = SF(qacc), *ctrl = SF(ctrl), *sens = SF(sens);
   auto fresh = [&](int k) { return mode == MODE_RESET && ((upd >> k) & 1u); };   // copy starts from qpos0
   auto has = [&](int k) { return ((live >> k) & 1u) != 0; };
@@ -279,6 +289,7 @@ MJB_DEV void run_env(const Ctx& c_in, const mjb_buffers& B, int venv, int num_en
     if (lane < dm.a1 * dm.store_f32) pre_sf = gsf[lane];
     if (lane == 0) pre_ts = B.timestep[e0];
   }
+  MJB_IMG_WAIT(c);
   MJB_G2S_WAIT();
   if (MJB_UNLIKELY(mode == MODE_RESET && dm.reset_noise > 0.f)) {
     // optional decorrelated starts (off by default: the reference always restarts at qpos0).  The draw is keyed by

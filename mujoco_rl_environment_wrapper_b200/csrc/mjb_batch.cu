@@ -44,7 +44,6 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
     mbar_expect_tx(bar, bytes);
     bulk_g2s(img, image, bytes, bar);
   }
-  mbar_wait(bar, 0);
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
   // MJB_LOCKSTEP: 2 rounds only, 1 rounds + every alignment point, 3 rounds replaced by a sync before the collision phase,
@@ -71,7 +70,9 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
       // (a masked reset lets warps skip their env, so intra-step alignment is off for it)
       c.cta_threads = (mask == nullptr ? 32 : 0) * (busy > warps ? warps : (busy < 0 ? 0 : busy));
     }
+    c.img_bar = r == 0 ? bar : nullptr;
     if (env < nvirt) run_env<PHYS, PACKED>(c, B, env_order ? env_order[env] : env + env_base, num_envs, mode, skip_frames, mask);
+    if (r == 0) mbar_wait(bar, 0);   // warps that had nothing to do in the first round (or returned early) have not waited yet
     if (lockstep) {
       if (groups > 1) {
         // the env-warps re-align in `groups` independent sets: fewer warps wait on the slowest env of a round,

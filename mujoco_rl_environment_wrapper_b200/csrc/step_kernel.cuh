@@ -89,6 +89,7 @@ struct Ctx {
   int align_all;        // CTA-level re-alignment points inside the step (bits): 1 constraints / Newton iterations, 2 before the
                         // collision phase, 4 after the Newton solve (the data-dependent part): see k_env
   float* probe_quat;    // this env's exported orientations in GLOBAL memory (4 floats per probe) or null
+  uint64_t* img_bar;    // first round of a launch: barrier of the image's bulk copy, waited on at the first use of the image (else null)
 #if defined(MJB_PHASE_PROF)
   long long* t_last;    // profiling build only: clock of the previous phase mark (lane 0)
 #endif
