@@ -47,8 +47,10 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
   float* scratch = reinterpret_cast<float*>(img + dm.image_words) + (size_t)warp * (dm.env_words + 4 * ((dm.nprobe + 3) & ~3));
   float* probe = scratch + dm.env_words;
   // MJB_LOCKSTEP: 2 rounds only, 1 rounds + every alignment point, 3 rounds replaced by a sync before the collision phase,
-  // 4 (default) rounds + re-alignment after the Newton solve, 5 = 4 + before the collision phase, 6 = 4 + Newton iterations
-  Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1 ? 7 : (lockstep == 3 ? 2 : (lockstep == 4 ? 4 : (lockstep == 5 ? 6 : (lockstep == 6 ? 5 : 0))))};
+  // 4 rounds + re-alignment after the Newton solve, 5 = 4 + before the collision phase, 6 = 4 + Newton iterations,
+  // 7 (default) re-alignment after the Newton solve ONLY: the env-warps leave it together and stay together through the
+  // tail of the step and the head of the next env without a barrier at the round boundary
+  Ctx c{&dm, img, scratch, lane, probe, 0, lockstep == 1 ? 7 : (lockstep == 3 ? 2 : ((lockstep == 4 || lockstep == 7) ? 4 : (lockstep == 5 ? 6 : (lockstep == 6 ? 5 : 0))))};
 #if defined(MJB_PHASE_PROF)
   long long t_last = clock64();
   c.t_last = &t_last;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(PHYS ? MJB_MAX_THREADS : 512, PHYS ? 1 : 4) k_
         const int gsz = (warps + groups - 1) / groups, g = warp / gsz;
         const int cnt = 32 * (g * gsz + gsz <= warps ? gsz : warps - g * gsz);
         asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "r"(cnt) : "memory");
-      } else if (lockstep != 3) __syncthreads();   // mode 3 aligns inside the step (before the collision phase) instead
+      } else if (lockstep != 3 && lockstep != 7) __syncthreads();   // modes 3 / 7 align inside the step only (before the collision phase / after the solve)
       MJB_PH(c, PH_BARRIER);
       env += stride;
     } else {
@@ -353,7 +355,7 @@ int mjb_batch_create(const mjb_model* m, const mjb_env_spec* spec, int32_t num_e
     mjb::set_error("mjb_batch_create: stream / event creation failed");
     return fail(MJB_ERR_CUDA);
   }
-  b->lockstep = mjb::env_int("MJB_LOCKSTEP", 4);
+  b->lockstep = mjb::env_int("MJB_LOCKSTEP", 7);
   b->groups = mjb::env_int("MJB_GROUPS", 1);
   if (b->groups < 1 || b->groups > 8 || b->lockstep != 2) b->groups = 1;
   const int A = dm.a1;
